@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- tokens/sec + accepted-tokens/step of lookahead decoding, Llama-2-7B shape, W=15 N=5 G=15.
+
+One "step" of the contract = one full generate() of `--max-new` tokens from a fixed synthetic prompt
+(the unit minimal.py:34-45 times).  `value` is whole-job tokens/s with the prompt ids already handed to
+the engine (device timed with CUDA events); `e2e` is the same metric through the reference-facing plugin
+surface (lade.augment_all(); lade.config_lade(...); model.generate(...)) with the prompt in pinned host
+memory and the output read back to the host inside the timed region.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload 7b|13b|tiny]
+
+Extra objects on the JSON line: `roofline` (lookahead-attention kernel, HBM bound, timed live with CUDA
+events), `cpu_baseline` (the oracle port of the reference's loop on the host cores, bounded sample),
+`clocks`, `accepted_tokens_per_step`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (model shape, W, N, G, prompt_len)
+    "7b": (dict(hidden=4096, layers=32, heads=32, kv_heads=32, inter=11008, vocab=32000, max_pos=4096,
+                rope_theta=10000.0, eps=1e-5), 15, 5, 15, 1024),
+    "13b": (dict(hidden=5120, layers=40, heads=40, kv_heads=40, inter=13824, vocab=32016, max_pos=16384,
+                 rope_theta=1000000.0, eps=1e-5), 20, 7, 20, 256),
+    "tiny": (dict(hidden=256, layers=2, heads=2, kv_heads=2, inter=688, vocab=32000, max_pos=2048,
+                  rope_theta=10000.0, eps=1e-5), 5, 3, 3, 64),
+}
+WORKLOAD_NAMES = {"7b": "Llama-2-7B-shaped random-init bf16, greedy", "13b": "CodeLlama-13B-shaped random-init bf16, greedy",
+                  "tiny": "tiny random-init Llama (2 layers, hidden 256), greedy"}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="7b", choices=sorted(WORKLOADS))
+    ap.add_argument("--prompt-len", type=int, default=None)
+    ap.add_argument("--max-new", type=int, default=256)
+    ap.add_argument("--attn-impl", type=int, default=0)
+    ap.add_argument("--attn-splits", type=int, default=0)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_model(shape, device):
+    import torch
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    cfg = LlamaConfig(
+        hidden_size=shape["hidden"], num_hidden_layers=shape["layers"], num_attention_heads=shape["heads"],
+        num_key_value_heads=shape["kv_heads"], intermediate_size=shape["inter"], vocab_size=shape["vocab"],
+        max_position_embeddings=shape["max_pos"], rms_norm_eps=shape["eps"], tie_word_embeddings=False,
+        attention_bias=False, hidden_act="silu",
+        rope_parameters={"rope_type": "default", "rope_theta": shape["rope_theta"]})
+    with torch.device("meta"):
+        model = LlamaForCausalLM(cfg)
+    model = model.to_empty(device=device).to(torch.bfloat16)
+    g = torch.Generator(device=device).manual_seed(0)
+    with torch.no_grad():
+        for name, p in model.named_parameters():      # normal(0, initializer_range) as modeling_llama.py:934-943
+            if p.dim() >= 2:
+                p.normal_(0.0, 0.02, generator=g)
+            else:
+                p.fill_(1.0)
+        if hasattr(model.model, "rotary_emb"):
+            re = model.model.rotary_emb
+            D = cfg.hidden_size // cfg.num_attention_heads
+            inv = 1.0 / (shape["rope_theta"] ** (torch.arange(0, D, 2, dtype=torch.float32) / D))
+            re.inv_freq = inv.to(device)
+            if hasattr(re, "original_inv_freq"):
+                re.original_inv_freq = inv.to(device)
+    model.eval()
+    model.generation_config.pad_token_id = 0
+    model.generation_config.eos_token_id = None
+    return model
+
+
+def attn_roofline(eng, shape, reps=5):
+    """Time the lookahead-attention kernel alone, back to back over every layer's cache (L x 2 x kv rows
+    > L2, so no launch re-reads a cache line of the previous ones), on the launching stream."""
+    import torch
+    from lookaheaddecoding_b200 import _cabi
+
+    lib = eng.lib
+    meta = eng.meta.cpu().tolist()
+    q_len, kv_len = meta[_cabi.M_Q_LEN], meta[_cabi.M_KV_LEN]
+    rows = eng.q_steady
+    qb = eng.qb if rows == eng.rows_cap else eng.qb.view(-1)[: eng.nh * rows * eng.D].view(eng.nh, rows, eng.D)
+    stream = torch.cuda.current_stream(eng.dev)
+
+    def one_pass():
+        for l in range(eng.L):
+            _cabi.check(lib.lade_attn_fwd(stream.cuda_stream, qb.data_ptr(), eng.kv[l, 0].data_ptr(), eng.kv[l, 1].data_ptr(),
+                                          eng.attn_out.data_ptr(), eng.rowdesc.data_ptr(), eng.meta.data_ptr(),
+                                          eng.attn_scratch.data_ptr(), rows, eng.nh, eng.nkv, eng.D, eng.kv_capacity,
+                                          eng.kv_capacity, eng.attn_splits, eng.attn_impl))
+    for _ in range(3):
+        one_pass()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        one_pass()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / (reps * eng.L)
+    # algorithmic bytes per launch: K,V cache read + Q read + new K,V read + O write
+    Hq, Hkv, D = eng.nh, eng.nkv, eng.D
+    bytes_alg = 2 * kv_len * Hkv * D * 2 + q_len * Hq * D * 2 + 2 * q_len * Hkv * D * 2 + q_len * Hq * D * 2
+    peak, how = measured_peaks()
+    achieved = bytes_alg / (us * 1e-6) / 1e9
+    return {"bound": "hbm", "kernel": "lade_attn_fwd", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(achieved / peak, 4), "traffic": None, "peak_source": how, "us_per_launch": round(us, 2),
+            "alg_bytes_per_launch": bytes_alg, "kv_len": kv_len, "q_len": q_len, "launches_timed": reps * eng.L}
+
+
+def cpu_baseline(shape, W, N, G, n_threads, budget_layers=(1, 2), prompt_len=64, max_new=12):
+    """Oracle port of the reference loop (oracle/, reference eager numerics) on the host cores, on a bounded
+    sample: full widths, `budget_layers` decoder layers, short prompt; per-step time is extrapolated
+    linearly in depth to the full layer count (t = a + b*L fitted on the two depths)."""
+    import torch
+    from oracle import llama_ref as LR
+    from oracle import lookahead as LA
+
+    torch.set_num_threads(n_threads)
+    times = {}
+    toks = steps = 0
+    for L in budget_layers:
+        cfg = dict(shape, layers=L)
+        w = LR.init_weights(cfg, seed=0, dtype=torch.bfloat16)
+        om = LR.OracleLlama(cfg, w)
+        g = torch.Generator().manual_seed(1)
+        prompt = torch.randint(3, shape["vocab"], (prompt_len,), generator=g).tolist()
+        t0 = time.time()
+        out, st = LA.greedy_lookahead(prompt, max_new, W, N, G, om.step_fn, om.compact_fn, rng=random.Random(0))
+        times[L] = (time.time() - t0) / st
+        toks, steps = len(out) - prompt_len, st
+        del om, w
+    (l1, l2) = budget_layers
+    b = (times[l2] - times[l1]) / (l2 - l1)
+    a = times[l1] - b * l1
+    t_full = a + b * shape["layers"]
+    return {"value": round((toks / steps) / t_full, 3), "unit": "tokens/s", "cores": n_threads, "kind": "port",
+            "sample": f"oracle port (reference eager numerics) on CPU: full widths, {l1} and {l2} of {shape['layers']} layers, "
+                      f"P={prompt_len}, {max_new} new tokens ({steps} steps); per-step time extrapolated linearly in depth "
+                      f"({times[l1]:.2f}s@{l1}L, {times[l2]:.2f}s@{l2}L -> {t_full:.2f}s/step), {toks / steps:.2f} tokens/step"}
+
+
+def main():
+    args = parse()
+    shape, W, N, G, P = WORKLOADS[args.workload]
+    if args.prompt_len:
+        P = args.prompt_len
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    config = {"workload": f"{WORKLOAD_NAMES[args.workload]}, W={W} N={N} G={G}, prompt {P} tokens, {args.max_new} new tokens "
+                          f"per generate()", "prompt_len": P, "max_new_tokens": args.max_new,
+              "parallelism": "single" if world == 1 else f"replicas x{world} (LP exchange lands later)",
+              "l2_policy": "inputs larger than L2 (weights 13 GB/step stream through; KV of 32 layers > 126 MB)"}
+    metric = "tokens/sec (wall-clock) and accepted-tokens/step, Llama-2-7B W=15 N=5 G=15" if args.workload == "7b" else \
+        f"tokens/sec (wall-clock) and accepted-tokens/step, {args.workload} W={W} N={N} G={G}"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n_threads = os.cpu_count() or 1
+        cb = cpu_baseline(shape, W, N, G, n_threads)
+        line = {"metric": metric, "value": cb["value"], "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config, "impl": "reference",
+                "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0,
+                                            "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import lade
+    from lookaheaddecoding_b200.decoding import CONFIG_MAP, get_engine
+
+    model = build_model(shape, dev)
+    os.environ["USE_LADE"] = "1"
+    lade.augment_all()
+    lade.config_lade(LEVEL=N, WINDOW_SIZE=W, GUESS_SET_SIZE=G, DEBUG=0)
+    CONFIG_MAP["MAX_TOTAL_LEN"] = P + args.max_new
+    overrides = {}
+    if args.attn_impl:
+        overrides["attn_impl"] = args.attn_impl
+    if args.attn_splits:
+        overrides["attn_splits"] = args.attn_splits
+    if args.no_graph:
+        overrides["use_cuda_graph"] = False
+    CONFIG_MAP["ENGINE_OVERRIDES"] = overrides
+    torch.manual_seed(1 + rank)
+    prompt_host = torch.randint(3, shape["vocab"], (1, P)).pin_memory()
+    prompt_list = prompt_host[0].tolist()
+    eng = get_engine(model, max_total_len=P + args.max_new)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also captures the steady-step CUDA graph)
+    for _ in range(max(args.warmup, 1)):
+        eng.generate(prompt_list, args.max_new, rng=random.Random(0))
+    barrier()
+
+    # ---- device-timed: prompt already with the engine
+    sampler = ClockSampler(local_rank)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    toks = steps = 0
+    launches0 = eng.launches
+    with sampler:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            out = eng.generate(prompt_list, args.max_new, rng=random.Random(0))
+            toks += len(out) - P
+            steps += eng.last_steps
+        e1.record()
+        barrier()
+        dev_ms = e0.elapsed_time(e1)
+        launches = eng.launches - launches0
+        # ---- end to end through the plugin surface: pinned host prompt -> generate() -> host ids
+        barrier()
+        t0 = time.perf_counter()
+        e2e_toks = 0
+        for _ in range(args.steps):
+            random.seed(0)
+            ids = prompt_host.to(dev, non_blocking=True)
+            o = model.generate(ids, attention_mask=torch.ones_like(ids), max_new_tokens=args.max_new, do_sample=False)
+            o_host = o.cpu()
+            e2e_toks += o_host.shape[1] - P
+        barrier()
+        e2e_s = time.perf_counter() - t0
+    t = torch.tensor([dev_ms, e2e_s, float(toks), float(e2e_toks), float(steps), float(launches)], device=dev, dtype=torch.float64)
+    if world > 1:
+        mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_s = mx[0].item(), mx[1].item()
+        toks, e2e_toks, steps, launches = sm[2].item(), sm[3].item(), sm[4].item(), sm[5].item()
+    if rank != 0:
+        return
+    roof = attn_roofline(eng, shape)
+    clocks = sampler.summary()
+    cb = None
+    if not args.no_cpu_baseline:
+        try:
+            cb = cpu_baseline(shape, W, N, G, os.cpu_count() or 1)
+        except Exception as ex:  # the baseline is reporting only; never hide the GPU numbers
+            cb = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+    value = toks / (dev_ms * 1e-3)
+    line = {
+        "metric": metric, "value": round(value, 2), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+        "accepted_tokens_per_step": round(toks / steps, 3), "decode_steps": int(steps),
+        "ms_per_decode_step": round(dev_ms / steps, 4),
+        "e2e": {"value": round(e2e_toks / e2e_s, 2), "unit": "tokens/s", "h2d_bytes_per_step": P * 8,
+                "d2h_bytes_per_step": (P + args.max_new) * 8 + int(steps / args.steps) * 48 * 4},
+        "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cb, "clocks": clocks,
+        "attn_impl": eng.attn_impl, "attn_splits": eng.attn_splits, "cuda_graph": eng.use_cuda_graph,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,203 @@
+/*
+ * lade_sm100.h -- C ABI of the B200-native lookahead/verification decoding step.
+ *
+ * Drop-in boundary for ONE hot path of hao-ai-lab/LookaheadDecoding ("lade"): the Jacobi lookahead +
+ * n-gram verification step.  Every entry point names the reference interface it replaces
+ * (paths relative to the reference checkout, file:line).  Plain C: device tensors are passed as raw
+ * device pointers (torch `tensor.data_ptr()`), `stream` is a `cudaStream_t` passed as void*.
+ *
+ * Conventions
+ *   - every function returns 0 (LADE_OK) or a negative LADE_E* code; no C++ exception crosses the
+ *     boundary, nothing calls exit().  `lade_strerror` maps codes to text; `lade_last_cuda_error`
+ *     returns the text of the last CUDA error seen by the calling thread's library calls.
+ *   - all work is stream-ordered on the caller's stream; no hidden synchronisation; every launch is
+ *     CUDA-graph capturable (per-step scalars such as the KV length live in device memory).
+ *   - ownership: the caller owns every tensor (weights, activations, KV cache, scratch); the library
+ *     owns only `LadeCtx` (device-resident int32 window / n-gram pool / token buffers).
+ *   - one `LadeCtx` per generate() call per rank, driven by a single host thread.
+ *
+ * Data layouts (all row-major, innermost last)
+ *   KV cache of one layer : K and V each [n_kv_heads][kv_capacity][head_dim] bf16
+ *   Q (post-RoPE)         : [n_heads][q_pad][head_dim] bf16
+ *   attention output      : [q_rows][n_heads*head_dim] bf16
+ *   step rows             : ids/pos/rowdesc int32 [q_pad]
+ *   step meta             : int32 [LADE_META_INTS] (indices LADE_M_*)
+ *   lm rows / argmax slots: int32 [lm_cap], lm_cap = 1 + (W+N-3) + G*(N-1):
+ *                             slot 0 = row predicting the next token, slots [1, 1+W+N-3) = rows of the
+ *                             newest window level, slots [1+W+N-3, lm_cap) = verification rows.
+ */
+#ifndef LADE_SM100_H_
+#define LADE_SM100_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LADE_OK 0
+#define LADE_EINVAL (-1)      /* bad argument / unsupported shape */
+#define LADE_ECUDA (-2)       /* a CUDA runtime call failed (see lade_last_cuda_error) */
+#define LADE_ENOMEM (-3)
+#define LADE_EUNSUPPORTED (-4)
+#define LADE_ESTATE (-5)      /* call sequence violated */
+
+/* row classes carried by the row descriptors (rowdesc = class<<30 | block<<15 | index) */
+#define LADE_ROW_PREFIX 0
+#define LADE_ROW_WINDOW 1
+#define LADE_ROW_GUESS 2
+#define LADE_ROW_PAD 3
+
+/* indices into the device-resident step meta record */
+enum {
+  LADE_M_Q_LEN = 0,       /* live rows of this step                                   */
+  LADE_M_KV_LEN = 1,      /* committed KV rows before this step                       */
+  LADE_M_N_INPUT = 2,     /* re-fed input rows (prompt length on the first step)      */
+  LADE_M_LEVEL_OFFSET = 3,/* modeling_llama.py:136                                    */
+  LADE_M_ALL_OFFSET = 4,  /* level_offset + dist_offset, modeling_llama.py:188        */
+  LADE_M_TINY = 5,        /* level_sizes[-1], modeling_llama.py:132                   */
+  LADE_M_N_LEVELS = 6,
+  LADE_M_N_GUESS_TOK = 7, /* len(guess_tokens)                                        */
+  LADE_M_IS_PREFILL = 8,
+  LADE_M_PHASE = 9,       /* 0 prefill step, 1 window-fill step, 2 steady step        */
+  LADE_M_Q_PAD = 10,      /* rows materialised (>= q_len; extra rows are PAD rows)    */
+  LADE_M_DONE = 11,       /* generation finished: the step is a no-op                 */
+  LADE_M_STEP = 12,
+  LADE_META_INTS = 16
+};
+
+/* per-step result record written by lade_accept_update (device int32[LADE_RES_INTS]) */
+enum {
+  LADE_R_N_EMIT = 0,      /* tokens appended to the output this step (<= N-1)         */
+  LADE_R_MAX_HIT = 1,
+  LADE_R_MAX_HIT_IDX = 2,
+  LADE_R_KV_SRC = 3,      /* first cache row of the accepted n-gram (decoding.py:1156)*/
+  LADE_R_KV_DST = 4,      /* kvcache_len                                              */
+  LADE_R_KV_LEN = 5,      /* committed rows after the step                            */
+  LADE_R_DONE = 6,
+  LADE_R_N_OUT = 7,       /* len(input_ids) after the step                            */
+  LADE_R_STEPS = 8,
+  LADE_R_N_GUESS = 9,     /* n-grams verified this step                               */
+  LADE_R_HITS = 16,       /* hits[0..N-2]                                             */
+  LADE_RES_INTS = 48
+};
+
+typedef struct LadeCtx LadeCtx;
+
+/* lade.config_lade(...) knobs (lade/utils.py:13-37) + model shape */
+typedef struct LadeConfig {
+  int32_t window_size;      /* WINDOW_SIZE (W)                                        */
+  int32_t level;            /* LEVEL (N) >= 3 (lade/decoding.py:902)                   */
+  int32_t guess_set_size;   /* GUESS_SET_SIZE (G) > 0; -1 (unbounded set) unsupported */
+  int32_t pool_from_prompt; /* POOL_FROM_PROMPT                                       */
+  int32_t vocab_size;
+  int32_t max_total_len;    /* capacity of the token buffers (prompt + new + N)       */
+  int32_t n_eos;            /* number of eos ids (0..4)                               */
+  int32_t eos_token_id[4];  /* eos_token_id[0] is the one decoding.py:1169 tests      */
+  int32_t dist_workers;     /* DIST_WORKERS (lookahead parallelism), 1 = off          */
+  int32_t rank;             /* LOCAL_RANK                                             */
+} LadeConfig;
+
+/* ---- context --------------------------------------------------------------------------------- */
+
+/* Allocates the device-resident decode state (window, n-gram pool, token buffers).
+ * Replaces the python locals of jacobi_greedy_search_multilevel, lade/decoding.py:854-916. */
+int lade_ctx_create(const LadeConfig* cfg, LadeCtx** out);
+int lade_ctx_destroy(LadeCtx* ctx);
+
+/* Start a generate() call: upload prompt ids and the initial lookahead window level 0
+ * (W+N-3 tokens, drawn by the caller exactly as lade/decoding.py:887-902 does, so the python
+ * `random` stream is consumed identically), clear the pool and, if POOL_FROM_PROMPT, fill it from
+ * the prompt (lade/decoding.py:104-127, :915-916).  Host pointers; copied before return is NOT
+ * guaranteed -- the buffers must stay valid until the stream reaches this point. */
+int lade_ctx_reset(LadeCtx* ctx, void* stream, const int32_t* prompt_host, int32_t n_prompt,
+                   const int32_t* window0_host, int32_t n_window0, int32_t max_length);
+
+/* ---- step layout ------------------------------------------------------------------------------ */
+
+/* Build the rows of the next step on device: token ids, position ids, row descriptors (mask classes),
+ * the lm_head row list and the step meta record.  `q_pad` rows are written (rows past the live count
+ * are PAD rows).  Replaces LlamaForCausalLM.jforward_multilevel's input assembly
+ * (lade/models/modeling_llama.py:1458-1511), the pool lookup of lade/decoding.py:948-954 and the
+ * scalar part of j_make_causal_mask_multilevel (modeling_llama.py:132-138). */
+int lade_step_layout(LadeCtx* ctx, void* stream, int32_t q_pad, int32_t* ids_out, int32_t* pos_out,
+                     int32_t* rowdesc_out, int32_t* lm_rows_out, int32_t* meta_out);
+
+/* Expected live row count of the upcoming step as a pure function of the step index (host side, no
+ * sync): prefill = P + W+N-3 ; fill step k ; steady = (N-1)*(W+G).  Returns the count or <0. */
+int lade_step_rows_bound(const LadeConfig* cfg, int32_t n_prompt, int32_t step_index);
+
+/* ---- floating-point kernels of the decoder layer ---------------------------------------------- */
+
+/* out = weight * bf16(x_f32 * rsqrt(mean(x^2)+eps)) with optional fused residual add
+ * (h = bf16(x + delta) is written to `h_out` first).  LlamaRMSNorm, modeling_llama.py:222-227 and the
+ * residual adds of LlamaDecoderLayer.forward :883-889. */
+int lade_rmsnorm(void* stream, const void* x, const void* delta /*nullable*/, const void* weight,
+                 void* h_out /*nullable unless delta*/, void* out, int32_t rows, int32_t hidden, float eps);
+
+/* Final-norm variant that gathers rows: out[i] = rmsnorm(x[rows_idx[i]] (+ delta[rows_idx[i]])). */
+int lade_rmsnorm_gather(void* stream, const void* x, const void* delta, const void* weight,
+                        const int32_t* rows_idx, void* out, int32_t n_rows, int32_t hidden, float eps);
+
+/* Rotary embedding + KV append: reads the fused QKV projection [rows][(Hq+2Hkv)*D], writes
+ * Q'[Hq][q_pad][D] and appends K', V to the layer's cache at rows kv_len + r (kv_len from `meta`).
+ * apply_rotary_pos_emb (modeling_llama.py:342-346, bf16 rounding of each product and of the sum) and
+ * the torch.cat KV append (:513-516). cos/sin: [max_pos][D] in the model dtype (:255-256,:264-265). */
+int lade_rope_append(void* stream, const void* qkv, const void* cos_tab, const void* sin_tab,
+                     const int32_t* pos, const int32_t* meta, void* q_out, void* k_cache, void* v_cache,
+                     int32_t rows, int32_t q_pad, int32_t n_heads, int32_t n_kv_heads, int32_t head_dim,
+                     int32_t kv_capacity, int32_t max_pos);
+
+/* Lookahead attention over the persistent KV cache (the roofline kernel).  softmax(QK^T/sqrt(D) +
+ * lookahead mask) V with the mask evaluated in registers from `rowdesc`/`meta`; all step rows see the
+ * committed cache.  Replaces LlamaAttention.forward's attention core (modeling_llama.py:520-541), the
+ * dense mask of j_make_causal_mask_multilevel (:115-207) and flash_attn_lade.flash_attn_func(...,
+ * lookahead=[...]) (:705-713).  `scratch` holds split-KV partials: lade_attn_scratch_bytes(). */
+int lade_attn_fwd(void* stream, const void* q, const void* k_cache, const void* v_cache, void* out,
+                  const int32_t* rowdesc, const int32_t* meta, void* scratch, int32_t q_pad,
+                  int32_t n_heads, int32_t n_kv_heads, int32_t head_dim, int32_t kv_capacity,
+                  int32_t kv_bound /* host upper bound of kv_len + q_len */, int32_t n_splits,
+                  int32_t impl /* 0 = default, 1 = mma.sync path, 2 = tcgen05 path */);
+int64_t lade_attn_scratch_bytes(int32_t q_pad, int32_t n_heads, int32_t head_dim, int32_t n_splits);
+
+/* act = bf16(silu(gate)) * up on the fused [rows][2*inter] projection.  LlamaMLP, modeling_llama.py:378. */
+int lade_swiglu(void* stream, const void* gate_up, void* out, int32_t rows, int32_t inter);
+
+/* ---- token selection / accept / pool update ---------------------------------------------------- */
+
+/* Row-wise argmax with lowest-index tie-break over bf16 logits [n_rows][vocab]
+ * (torch.argmax at lade/decoding.py:1021,1041,1052,1072,1102). */
+int lade_argmax_rows(void* stream, const void* logits, int32_t n_rows, int32_t vocab, int32_t ld,
+                     int32_t* out_idx);
+
+/* Verification + state update of one step, fully on device: longest-prefix accept
+ * (lade/decoding.py:1071-1084), window fill / shift (:1038-1066,:1119-1124), n-gram pool LRU update
+ * (:37-63,:1116), emission with the EOS scan and POOL_FROM_PROMPT appends (:1165-1177), stopping
+ * (:1205-1219).  `argmax_slots` uses the lm-row slot layout above.  Writes `result` (LADE_R_*). */
+int lade_accept_update(LadeCtx* ctx, void* stream, const int32_t* argmax_slots, const int32_t* meta,
+                       int32_t* result);
+
+/* Move the accepted n-gram's K/V rows to the cache tail for every layer (lade/decoding.py:1156-1163).
+ * k_base/v_base point at layer 0; layers are `layer_stride_elems` apart. */
+int lade_kv_compact(void* stream, const int32_t* result, void* k_base, void* v_base,
+                    int64_t layer_stride_elems, int32_t n_layers, int32_t n_kv_heads,
+                    int32_t kv_capacity, int32_t head_dim, int32_t max_rows);
+
+/* Copy the generated ids (device) out: out_ids_dev int32[max_total_len]; count via result. */
+int lade_ctx_output_ids(LadeCtx* ctx, void* stream, int32_t* out_host, int32_t n);
+/* Debug/test access to the device state (pool snapshot for parity tests). */
+int lade_ctx_pool_snapshot(LadeCtx* ctx, void* stream, int32_t* cnt_host, int32_t* tup_host);
+int lade_ctx_window_snapshot(LadeCtx* ctx, void* stream, int32_t* win_host, int32_t* len_host);
+
+/* ---- lookahead parallelism (lade_distributed; lade/decoding.py:956-984,1088-1107) --------------- */
+/* LP record of one rank for one step: [max_hit, hits[N-1], n_new, new_results slice...]. */
+int lade_lp_record_ints(const LadeConfig* cfg);
+
+const char* lade_strerror(int code);
+const char* lade_last_cuda_error(void);
+int lade_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LADE_SM100_H_ */

@@ -1,0 +1,35 @@
+// C-ABI dispatch of the lookahead attention kernels.
+#include "common.cuh"
+
+namespace lade {
+int attn_fwd_mma_launch(cudaStream_t stream, const void* q, const void* k_cache, const void* v_cache, void* out,
+                        const int32_t* rowdesc, const int32_t* meta, void* scratch, int q_pad, int n_heads,
+                        int n_kv_heads, int head_dim, int kv_capacity, int n_splits);
+int attn_fwd_tc_launch(cudaStream_t stream, const void* q, const void* k_cache, const void* v_cache, void* out,
+                       const int32_t* rowdesc, const int32_t* meta, void* scratch, int q_pad, int n_heads,
+                       int n_kv_heads, int head_dim, int kv_capacity, int kv_bound, int n_splits);
+}  // namespace lade
+
+extern "C" {
+
+int64_t lade_attn_scratch_bytes(int32_t q_pad, int32_t n_heads, int32_t head_dim, int32_t n_splits) {
+  if (q_pad < 1 || n_heads < 1 || head_dim < 1 || n_splits < 1) return LADE_EINVAL;
+  const int64_t rows_pad = (int64_t)((q_pad + 127) / 128) * 128;
+  return 16384 * 4 + (int64_t)n_splits * n_heads * rows_pad * (head_dim + 2) * 4;
+}
+
+int lade_attn_fwd(void* stream, const void* q, const void* k_cache, const void* v_cache, void* out,
+                  const int32_t* rowdesc, const int32_t* meta, void* scratch, int32_t q_pad,
+                  int32_t n_heads, int32_t n_kv_heads, int32_t head_dim, int32_t kv_capacity,
+                  int32_t kv_bound, int32_t n_splits, int32_t impl) {
+  if (!q || !k_cache || !v_cache || !out || !rowdesc || !meta || !scratch) return LADE_EINVAL;
+  if (q_pad < 1 || n_heads < 1 || n_kv_heads < 1 || n_heads % n_kv_heads != 0 || n_splits < 1 || kv_capacity < 1)
+    return LADE_EINVAL;
+  if (impl == 2)
+    return lade::attn_fwd_tc_launch((cudaStream_t)stream, q, k_cache, v_cache, out, rowdesc, meta, scratch, q_pad,
+                                    n_heads, n_kv_heads, head_dim, kv_capacity, kv_bound, n_splits);
+  return lade::attn_fwd_mma_launch((cudaStream_t)stream, q, k_cache, v_cache, out, rowdesc, meta, scratch, q_pad,
+                                   n_heads, n_kv_heads, head_dim, kv_capacity, n_splits);
+}
+
+}  // extern "C"

@@ -1,0 +1,204 @@
+// Memory-bound glue kernels of the decoder layer, with the reference's bf16 rounding points.
+//   RMSNorm (+ fused residual add)   lade/models/modeling_llama.py:222-227, :883-889
+//   rotary embedding + KV append     lade/models/modeling_llama.py:342-346, :513-516
+//   SwiGLU                            lade/models/modeling_llama.py:378
+// All are HBM-bound byte movers: 16-byte vectorised, coalesced, one pass over the data.
+#include "common.cuh"
+
+namespace lade {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One CTA per row.  h = bf16(x + delta) (if delta), out = w * bf16(h_f32 * rsqrt(mean(h^2) + eps)).
+template <bool GATHER>
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const __nv_bfloat16* __restrict__ x,
+                                                      const __nv_bfloat16* __restrict__ delta,
+                                                      const __nv_bfloat16* __restrict__ w,
+                                                      const int* __restrict__ rows_idx,
+                                                      __nv_bfloat16* __restrict__ h_out,
+                                                      __nv_bfloat16* __restrict__ out, int hidden, float eps) {
+  extern __shared__ float s_row[];  // hidden floats
+  __shared__ float s_part[8];
+  const int out_row = blockIdx.x;
+  const int in_row = GATHER ? rows_idx[out_row] : out_row;
+  const __nv_bfloat16* xr = x + (long long)in_row * hidden;
+  const __nv_bfloat16* dr = delta ? delta + (long long)in_row * hidden : nullptr;
+  const int nvec = hidden / 8;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    uint4 v = reinterpret_cast<const uint4*>(xr)[i];
+    __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(&v);
+    float f[8];
+    if (dr) {
+      uint4 dv = reinterpret_cast<const uint4*>(dr)[i];
+      const __nv_bfloat16* de = reinterpret_cast<const __nv_bfloat16*>(&dv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        e[j] = __float2bfloat16_rn(__bfloat162float(e[j]) + __bfloat162float(de[j]));   // residual add in bf16
+        f[j] = __bfloat162float(e[j]);
+      }
+      if (h_out && !GATHER) reinterpret_cast<uint4*>(h_out + (long long)out_row * hidden)[i] = v;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = __bfloat162float(e[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s_row[i * 8 + j] = f[j];
+      ss += f[j] * f[j];
+    }
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += s_part[k];
+  const float rstd = rsqrtf(tot / (float)hidden + eps);
+  __nv_bfloat16* orow = out + (long long)out_row * hidden;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    uint4 wv = reinterpret_cast<const uint4*>(w)[i];
+    const __nv_bfloat16* we = reinterpret_cast<const __nv_bfloat16*>(&wv);
+    uint4 ov;
+    __nv_bfloat16* oe = reinterpret_cast<__nv_bfloat16*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float n = bf16_round(s_row[i * 8 + j] * rstd);                 // .to(input_dtype)
+      oe[j] = __float2bfloat16_rn(__bfloat162float(we[j]) * n);           // weight * hidden (bf16 mul)
+    }
+    reinterpret_cast<uint4*>(orow)[i] = ov;
+  }
+}
+
+// RoPE + append.  grid: (rows, Hq + 2*Hkv) ; block: D/2 threads (one rotation pair each, D <= 256).
+__global__ void rope_append_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ cos_tab,
+                                   const __nv_bfloat16* __restrict__ sin_tab, const int* __restrict__ pos,
+                                   const int* __restrict__ meta, __nv_bfloat16* __restrict__ q_out,
+                                   __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache,
+                                   int q_pad, int n_heads, int n_kv_heads, int D, int kv_capacity, int max_pos) {
+  const int r = blockIdx.x;
+  const int h = blockIdx.y;
+  const int t = threadIdx.x;  // pair index in [0, D/2)
+  const int half = D >> 1;
+  const int ld = (n_heads + 2 * n_kv_heads) * D;
+  const __nv_bfloat16* src = qkv + (long long)r * ld + (long long)h * D;
+  const int kv_len = meta[LADE_M_KV_LEN];
+  const int cache_row = kv_len + r;
+  if (h >= n_heads + n_kv_heads) {  // V: plain append
+    const int hv = h - n_heads - n_kv_heads;
+    if (cache_row < kv_capacity) {
+      __nv_bfloat16* dst = v_cache + ((long long)hv * kv_capacity + cache_row) * D;
+      dst[t] = src[t];
+      dst[t + half] = src[t + half];
+    }
+    return;
+  }
+  int p = pos[r];
+  p = p < 0 ? 0 : (p >= max_pos ? max_pos - 1 : p);
+  const float x1 = __bfloat162float(src[t]);
+  const float x2 = __bfloat162float(src[t + half]);
+  const float c1 = __bfloat162float(cos_tab[(long long)p * D + t]);
+  const float c2 = __bfloat162float(cos_tab[(long long)p * D + t + half]);
+  const float s1 = __bfloat162float(sin_tab[(long long)p * D + t]);
+  const float s2 = __bfloat162float(sin_tab[(long long)p * D + t + half]);
+  // (q * cos) + (rotate_half(q) * sin), every op rounded to bf16 (modeling_llama.py:344-345)
+  const float o1 = bf16_round(bf16_round(x1 * c1) + bf16_round(-x2 * s1));
+  const float o2 = bf16_round(bf16_round(x2 * c2) + bf16_round(x1 * s2));
+  __nv_bfloat16* dst;
+  if (h < n_heads) {
+    dst = q_out + ((long long)h * q_pad + r) * D;
+  } else {
+    if (cache_row >= kv_capacity) return;
+    dst = k_cache + ((long long)(h - n_heads) * kv_capacity + cache_row) * D;
+  }
+  dst[t] = __float2bfloat16_rn(o1);
+  dst[t + half] = __float2bfloat16_rn(o2);
+}
+
+__global__ void swiglu_kernel(const __nv_bfloat16* __restrict__ gate_up, __nv_bfloat16* __restrict__ out,
+                              int rows, int inter) {
+  const int nvec = inter / 8;
+  const long long total = (long long)rows * nvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / nvec), c = (int)(i % nvec);
+    const uint4 gv = reinterpret_cast<const uint4*>(gate_up + (long long)r * 2 * inter)[c];
+    const uint4 uv = reinterpret_cast<const uint4*>(gate_up + (long long)r * 2 * inter + inter)[c];
+    const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(&gv);
+    const __nv_bfloat16* u = reinterpret_cast<const __nv_bfloat16*>(&uv);
+    uint4 ov;
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(&ov);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float x = __bfloat162float(g[j]);
+      const float s = bf16_round(x / (1.0f + expf(-x)));                    // silu in fp32, bf16 result
+      o[j] = __float2bfloat16_rn(s * __bfloat162float(u[j]));
+    }
+    reinterpret_cast<uint4*>(out + (long long)r * inter)[c] = ov;
+  }
+}
+
+}  // namespace lade
+
+using namespace lade;
+
+extern "C" {
+
+int lade_rmsnorm(void* stream, const void* x, const void* delta, const void* weight, void* h_out, void* out,
+                 int32_t rows, int32_t hidden, float eps) {
+  if (!x || !weight || !out || rows < 1 || hidden < 8 || hidden % 8 != 0) return LADE_EINVAL;
+  if (delta && !h_out) return LADE_EINVAL;
+  const size_t smem = sizeof(float) * hidden;
+  if (smem > 96 * 1024) return LADE_EUNSUPPORTED;
+  if (smem > 48 * 1024)
+    LADE_CUDA_CHECK(cudaFuncSetAttribute(rmsnorm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rmsnorm_kernel<false><<<rows, 256, smem, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)delta, (const __nv_bfloat16*)weight, nullptr,
+      (__nv_bfloat16*)h_out, (__nv_bfloat16*)out, hidden, eps);
+  LADE_LAUNCH_CHECK("rmsnorm_kernel");
+  return LADE_OK;
+}
+
+int lade_rmsnorm_gather(void* stream, const void* x, const void* delta, const void* weight,
+                        const int32_t* rows_idx, void* out, int32_t n_rows, int32_t hidden, float eps) {
+  if (!x || !weight || !out || !rows_idx || n_rows < 1 || hidden < 8 || hidden % 8 != 0) return LADE_EINVAL;
+  const size_t smem = sizeof(float) * hidden;
+  if (smem > 96 * 1024) return LADE_EUNSUPPORTED;
+  if (smem > 48 * 1024)
+    LADE_CUDA_CHECK(cudaFuncSetAttribute(rmsnorm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  rmsnorm_kernel<true><<<n_rows, 256, smem, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)delta, (const __nv_bfloat16*)weight, rows_idx, nullptr,
+      (__nv_bfloat16*)out, hidden, eps);
+  LADE_LAUNCH_CHECK("rmsnorm_gather_kernel");
+  return LADE_OK;
+}
+
+int lade_rope_append(void* stream, const void* qkv, const void* cos_tab, const void* sin_tab,
+                     const int32_t* pos, const int32_t* meta, void* q_out, void* k_cache, void* v_cache,
+                     int32_t rows, int32_t q_pad, int32_t n_heads, int32_t n_kv_heads, int32_t head_dim,
+                     int32_t kv_capacity, int32_t max_pos) {
+  if (!qkv || !cos_tab || !sin_tab || !pos || !meta || !q_out || !k_cache || !v_cache) return LADE_EINVAL;
+  if (rows < 1 || rows > q_pad || head_dim % 2 != 0 || head_dim > 512 || n_heads < 1 || n_kv_heads < 1) return LADE_EINVAL;
+  dim3 grid(rows, n_heads + 2 * n_kv_heads);
+  rope_append_kernel<<<grid, head_dim / 2, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)cos_tab, (const __nv_bfloat16*)sin_tab, pos, meta,
+      (__nv_bfloat16*)q_out, (__nv_bfloat16*)k_cache, (__nv_bfloat16*)v_cache, q_pad, n_heads, n_kv_heads,
+      head_dim, kv_capacity, max_pos);
+  LADE_LAUNCH_CHECK("rope_append_kernel");
+  return LADE_OK;
+}
+
+int lade_swiglu(void* stream, const void* gate_up, void* out, int32_t rows, int32_t inter) {
+  if (!gate_up || !out || rows < 1 || inter < 8 || inter % 8 != 0) return LADE_EINVAL;
+  const long long total = (long long)rows * (inter / 8);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  swiglu_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)gate_up, (__nv_bfloat16*)out, rows, inter);
+  LADE_LAUNCH_CHECK("swiglu_kernel");
+  return LADE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,329 @@
+"""Host-side driver of the B200 lookahead/verification step.
+
+One ``LookaheadEngine`` wraps one HF ``LlamaForCausalLM`` on one GPU.  Per decoding step it launches
+(through the C-ABI of ``include/lade_sm100.h``):
+
+    lade_step_layout -> embedding gather -> L x [ lade_rmsnorm -> QKV GEMM -> lade_rope_append ->
+    lade_attn_fwd -> O GEMM -> lade_rmsnorm(+residual) -> gate/up GEMM -> lade_swiglu -> down GEMM ]
+    -> lade_rmsnorm_gather (live lm_head rows only) -> lm_head GEMM -> lade_argmax_rows ->
+    lade_accept_update -> lade_kv_compact
+
+which is the B200 re-design of one iteration of the reference's ``while True`` loop
+(``lade/decoding.py:923-1219``) including ``jforward_multilevel``
+(``lade/models/modeling_llama.py:1381-1608``).  The dense projections are plain library GEMMs
+(cuBLAS through ``torch.mm``); everything else is this repo's CUDA.  All per-step scalars live in
+device memory, so the steady step is a fixed-shape launch sequence that is captured once in a CUDA
+graph and replayed; the host reads back one 48-int record per step (accepted tokens + done flag).
+
+PyTorch is used for device memory, streams and the GEMMs only.  There is no CPU fallback: a missing
+library or a non-CUDA model raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import random
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import LadeConfig, LadeError, check
+
+
+@dataclass
+class StepRecord:
+    n_emit: int
+    max_hit: int
+    hits: List[int]
+    n_guess: int
+    kv_len: int
+    done: bool
+
+
+def _ptr(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+class LookaheadEngine:
+    """Device-resident lookahead decoding for one Llama model (batch 1, bf16, CUDA)."""
+
+    def __init__(self, model, window_size: int, level: int, guess_set_size: int,
+                 pool_from_prompt: bool = False, max_total_len: int = 4096, attn_impl: int = 0,
+                 attn_splits: Optional[int] = None, use_cuda_graph: bool = True, debug: bool = False):
+        self.lib = _cabi.load()
+        cfg = model.config
+        p0 = next(model.parameters())
+        if p0.device.type != "cuda":
+            raise LadeError("LookaheadEngine needs the model on a CUDA device (no CPU fallback)")
+        if p0.dtype != torch.bfloat16:
+            raise LadeError(f"LookaheadEngine supports bf16 models only (got {p0.dtype})")
+        if level < 3:
+            raise LadeError("LEVEL must be >= 3 (lade/decoding.py:902)")
+        if guess_set_size == -1:
+            raise LadeError("GUESS_SET_SIZE=-1 (unbounded python set) is not supported on device")
+        self.model = model
+        self.dev = p0.device
+        self.W, self.N, self.G = int(window_size), int(level), int(guess_set_size)
+        self.GS = self.N - 1
+        self.WCAP = self.W + self.N - 3
+        self.pool_from_prompt = bool(pool_from_prompt)
+        self.H = cfg.hidden_size
+        self.L = cfg.num_hidden_layers
+        self.nh = cfg.num_attention_heads
+        self.nkv = getattr(cfg, "num_key_value_heads", None) or self.nh
+        self.D = getattr(cfg, "head_dim", None) or self.H // self.nh
+        self.I = cfg.intermediate_size
+        self.V = cfg.vocab_size
+        self.eps = float(cfg.rms_norm_eps)
+        if self.D != 128:
+            raise LadeError(f"head_dim {self.D} unsupported (the sm_100a attention kernel is built for 128)")
+        self.max_pos = int(getattr(cfg, "max_position_embeddings", 4096))
+        rp = getattr(cfg, "rope_parameters", None) or {}
+        self.rope_theta = float(rp.get("rope_theta", getattr(cfg, "rope_theta", 10000.0)) if isinstance(rp, dict)
+                                else getattr(cfg, "rope_theta", 10000.0))
+        self.attn_impl = attn_impl
+        self.use_cuda_graph = use_cuda_graph
+        self.debug = debug
+        self.lm_cap = 1 + self.WCAP + self.G * self.GS
+        self.q_steady = self.GS * (self.W + max(self.G, 0))
+        self.max_total_len = int(max_total_len)
+        self.kv_capacity = self.max_total_len + self.q_steady + self.WCAP + 8
+        sm = torch.cuda.get_device_properties(self.dev).multi_processor_count
+        q_tiles = (self.q_steady + 127) // 128
+        self.attn_splits = int(attn_splits) if attn_splits else max(1, -(-sm // (self.nh * q_tiles)))
+
+        self._fuse_weights()
+        self._rope_tables()
+        self._alloc(self.q_steady)
+        self._ctx = C.c_void_p()
+        self._lcfg = None
+        self._graph = None
+        self._pinned_res = torch.empty(_cabi.RES_INTS, dtype=torch.int32, pin_memory=True)
+        self.launches = 0   # kernels of THIS repo launched (graph replays counted by their content)
+        self._launches_per_graph = 0
+        self.last_steps = 0
+        self.last_records: List[StepRecord] = []
+
+    # ------------------------------------------------------------------------------------------
+    def _fuse_weights(self):
+        """Fuse q/k/v and gate/up into single GEMM operands; re-point the HF parameters at views of
+        the fused storage so no second copy of the weights stays resident."""
+        m = self.model.model
+        self.embed = m.embed_tokens.weight
+        self.norm_w = m.norm.weight
+        self.lm_head = self.model.lm_head.weight
+        self.w_qkv, self.w_o, self.w_gu, self.w_down, self.ln1, self.ln2 = [], [], [], [], [], []
+        with torch.no_grad():
+            for layer in m.layers:
+                a, mlp = layer.self_attn, layer.mlp
+                if getattr(a.q_proj, "bias", None) is not None:
+                    raise LadeError("attention_bias=True is not supported")
+                qkv = torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], dim=0).contiguous()
+                nq, nk = a.q_proj.weight.shape[0], a.k_proj.weight.shape[0]
+                a.q_proj.weight.data = qkv[:nq]
+                a.k_proj.weight.data = qkv[nq:nq + nk]
+                a.v_proj.weight.data = qkv[nq + nk:]
+                gu = torch.cat([mlp.gate_proj.weight, mlp.up_proj.weight], dim=0).contiguous()
+                mlp.gate_proj.weight.data = gu[: self.I]
+                mlp.up_proj.weight.data = gu[self.I:]
+                self.w_qkv.append(qkv)
+                self.w_gu.append(gu)
+                self.w_o.append(a.o_proj.weight)
+                self.w_down.append(mlp.down_proj.weight)
+                self.ln1.append(layer.input_layernorm.weight)
+                self.ln2.append(layer.post_attention_layernorm.weight)
+
+    def _rope_tables(self):
+        # fp32 math then cast to the model dtype: lade/models/modeling_llama.py:240-256,:264-265
+        D = self.D
+        inv_freq = 1.0 / (self.rope_theta ** (torch.arange(0, D, 2).float() / D))
+        # the reference regrows its table on demand (:258-261); size ours for the longest sequence
+        self.table_len = max(self.max_pos, self.max_total_len + self.WCAP + self.N + 8)
+        t = torch.arange(self.table_len, dtype=inv_freq.dtype)
+        freqs = torch.outer(t, inv_freq)
+        emb = torch.cat((freqs, freqs), dim=-1)
+        self.cos = emb.cos().to(torch.bfloat16).to(self.dev).contiguous()
+        self.sin = emb.sin().to(torch.bfloat16).to(self.dev).contiguous()
+
+    def _alloc(self, rows: int):
+        dev, bf = self.dev, torch.bfloat16
+        self.rows_cap = rows
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.ids = torch.zeros(rows, **i32)
+        self.pos = torch.zeros(rows, **i32)
+        self.rowdesc = torch.zeros(rows, **i32)
+        self.meta = torch.zeros(_cabi.META_INTS, **i32)
+        self.lm_rows = torch.zeros(self.lm_cap, **i32)
+        self.am = torch.zeros(self.lm_cap, **i32)
+        self.res = torch.zeros(_cabi.RES_INTS, **i32)
+        self.h = torch.empty(rows, self.H, dtype=bf, device=dev)
+        self.xn = torch.empty(rows, self.H, dtype=bf, device=dev)
+        self.qkv = torch.empty(rows, (self.nh + 2 * self.nkv) * self.D, dtype=bf, device=dev)
+        self.qb = torch.zeros(self.nh, rows, self.D, dtype=bf, device=dev)
+        self.attn_out = torch.empty(rows, self.nh * self.D, dtype=bf, device=dev)
+        self.o_buf = torch.empty(rows, self.H, dtype=bf, device=dev)
+        self.gu = torch.empty(rows, 2 * self.I, dtype=bf, device=dev)
+        self.act = torch.empty(rows, self.I, dtype=bf, device=dev)
+        self.d_buf = torch.empty(rows, self.H, dtype=bf, device=dev)
+        self.xn_lm = torch.empty(self.lm_cap, self.H, dtype=bf, device=dev)
+        self.logits = torch.empty(self.lm_cap, self.V, dtype=bf, device=dev)
+        if not hasattr(self, "kv"):
+            self.kv = torch.zeros(self.L, 2, self.nkv, self.kv_capacity, self.D, dtype=bf, device=dev)
+        nbytes = self.lib.lade_attn_scratch_bytes(rows, self.nh, self.D, self.attn_splits)
+        self.attn_scratch = torch.zeros(int(nbytes), dtype=torch.uint8, device=dev)
+
+    # ------------------------------------------------------------------------------------------
+    def _ensure_ctx(self, eos_ids: Sequence[int]):
+        eos_ids = list(eos_ids)[:4]
+        key = (tuple(eos_ids),)
+        if self._lcfg is not None and self._ctx_key == key:
+            return
+        if self._ctx:
+            self.lib.lade_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+            self._graph = None
+        c = LadeConfig()
+        c.window_size, c.level, c.guess_set_size = self.W, self.N, self.G
+        c.pool_from_prompt = int(self.pool_from_prompt)
+        c.vocab_size = self.V
+        c.max_total_len = self.max_total_len + self.N + 8
+        c.n_eos = len(eos_ids)
+        for i, e in enumerate(eos_ids):
+            c.eos_token_id[i] = int(e)
+        c.dist_workers, c.rank = 1, 0
+        check(self.lib.lade_ctx_create(C.byref(c), C.byref(self._ctx)), "lade_ctx_create")
+        self._lcfg = c
+        self._ctx_key = key
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self.lib.lade_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def _launch_step(self, rows: int, stream: int):
+        """All launches of one step on `stream` for `rows` materialised rows (rows <= rows_cap)."""
+        lib, L = self.lib, self.L
+        n = 0
+        check(lib.lade_step_layout(self._ctx, stream, rows, _ptr(self.ids), _ptr(self.pos), _ptr(self.rowdesc),
+                                   _ptr(self.lm_rows), _ptr(self.meta)), "lade_step_layout"); n += 1
+        h = self.h[:rows]
+        torch.index_select(self.embed, 0, self.ids[:rows], out=h)
+        xn, qkv, attn_out = self.xn[:rows], self.qkv[:rows], self.attn_out[:rows]
+        o_buf, gu, act, d_buf = self.o_buf[:rows], self.gu[:rows], self.act[:rows], self.d_buf[:rows]
+        qb = self.qb if rows == self.rows_cap else self.qb.view(-1)[: self.nh * rows * self.D].view(self.nh, rows, self.D)
+        delta = None
+        kv_bound = self.kv_capacity
+        for l in range(L):
+            check(lib.lade_rmsnorm(stream, _ptr(h), _ptr(delta), _ptr(self.ln1[l]), _ptr(h) if delta is not None else 0,
+                                   _ptr(xn), rows, self.H, self.eps), "lade_rmsnorm"); n += 1
+            torch.mm(xn, self.w_qkv[l].t(), out=qkv)
+            kc, vc = self.kv[l, 0], self.kv[l, 1]
+            check(lib.lade_rope_append(stream, _ptr(qkv), _ptr(self.cos), _ptr(self.sin), _ptr(self.pos), _ptr(self.meta),
+                                       _ptr(qb), _ptr(kc), _ptr(vc), rows, rows, self.nh, self.nkv, self.D,
+                                       self.kv_capacity, self.table_len), "lade_rope_append"); n += 1
+            check(lib.lade_attn_fwd(stream, _ptr(qb), _ptr(kc), _ptr(vc), _ptr(attn_out), _ptr(self.rowdesc),
+                                    _ptr(self.meta), _ptr(self.attn_scratch), rows, self.nh, self.nkv, self.D,
+                                    self.kv_capacity, kv_bound, self.attn_splits, self.attn_impl), "lade_attn_fwd"); n += 1
+            torch.mm(attn_out, self.w_o[l].t(), out=o_buf)
+            check(lib.lade_rmsnorm(stream, _ptr(h), _ptr(o_buf), _ptr(self.ln2[l]), _ptr(h), _ptr(xn), rows, self.H,
+                                   self.eps), "lade_rmsnorm"); n += 1
+            torch.mm(xn, self.w_gu[l].t(), out=gu)
+            check(lib.lade_swiglu(stream, _ptr(gu), _ptr(act), rows, self.I), "lade_swiglu"); n += 1
+            torch.mm(act, self.w_down[l].t(), out=d_buf)
+            delta = d_buf
+        check(lib.lade_rmsnorm_gather(stream, _ptr(h), _ptr(delta), _ptr(self.norm_w), _ptr(self.lm_rows),
+                                      _ptr(self.xn_lm), self.lm_cap, self.H, self.eps), "lade_rmsnorm_gather"); n += 1
+        torch.mm(self.xn_lm, self.lm_head.t(), out=self.logits)
+        check(lib.lade_argmax_rows(stream, _ptr(self.logits), self.lm_cap, self.V, self.V, _ptr(self.am)),
+              "lade_argmax_rows"); n += 1
+        check(lib.lade_accept_update(self._ctx, stream, _ptr(self.am), _ptr(self.meta), _ptr(self.res)),
+              "lade_accept_update"); n += 1
+        check(lib.lade_kv_compact(stream, _ptr(self.res), _ptr(self.kv[0, 0]), _ptr(self.kv[0, 1]),
+                                  self.kv.stride(0), self.L, self.nkv, self.kv_capacity, self.D, max(self.GS - 1, 1)),
+              "lade_kv_compact"); n += 1
+        return n
+
+    def _read_result(self) -> StepRecord:
+        self._pinned_res.copy_(self.res, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        r = self._pinned_res.numpy()
+        n_emit = int(r[_cabi.R_N_EMIT])
+        return StepRecord(n_emit=n_emit, max_hit=int(r[_cabi.R_MAX_HIT]),
+                          hits=[int(x) for x in r[_cabi.R_HITS:_cabi.R_HITS + n_emit]],
+                          n_guess=int(r[_cabi.R_N_GUESS]), kv_len=int(r[_cabi.R_KV_LEN]), done=bool(r[_cabi.R_DONE]))
+
+    def _steady_graph(self):
+        if self._graph is not None:
+            return self._graph
+        rows = self.q_steady
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                self._launches_per_graph = self._launch_step(rows, torch.cuda.current_stream(self.dev).cuda_stream)
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        self._graph = g
+        return g
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def generate(self, prompt_ids: Sequence[int], max_new_tokens: int, eos_token_ids: Sequence[int] = (),
+                 rng: Optional[random.Random] = None, window0: Optional[Sequence[int]] = None) -> List[int]:
+        """Greedy lookahead decoding; returns prompt + generated ids (trimmed to P + max_new_tokens).
+
+        The initial window is drawn on the host exactly as lade/decoding.py:887-902 does
+        (``random.choice`` over the prompt, W+N-3 draws) so the python RNG stream matches the reference.
+        """
+        prompt = [int(t) for t in prompt_ids]
+        P = len(prompt)
+        max_length = P + int(max_new_tokens)
+        if max_length > self.max_total_len:
+            raise LadeError(f"prompt+max_new_tokens={max_length} exceeds engine capacity {self.max_total_len}")
+        self._ensure_ctx(eos_token_ids)
+        rnd = rng or random
+        if window0 is None:
+            window0 = [rnd.choice(prompt) for _ in range(self.WCAP)]
+        stream = torch.cuda.current_stream(self.dev).cuda_stream
+        prompt_np = np.asarray(prompt, dtype=np.int32)
+        win_np = np.asarray(list(window0), dtype=np.int32)
+        check(self.lib.lade_ctx_reset(self._ctx, stream, prompt_np.ctypes.data, P, win_np.ctypes.data, len(win_np),
+                                      max_length), "lade_ctx_reset")
+        torch.cuda.current_stream(self.dev).synchronize()   # host buffers were consumed
+        self.launches += 2 + int(self.pool_from_prompt)
+        rows0 = P + self.WCAP
+        if rows0 > self.rows_cap:
+            self._graph = None
+            self._alloc(rows0)
+        out = list(prompt)
+        self.last_records = []
+        step = 0
+        done = False
+        while not done:
+            if step <= self.N - 3 or not self.use_cuda_graph:
+                rows = self.lib.lade_step_rows_bound(C.byref(self._lcfg), P, step)
+                if rows < 0:
+                    raise LadeError("lade_step_rows_bound failed")
+                rows = min(rows, self.rows_cap)
+                self.launches += self._launch_step(rows, stream)
+            else:
+                self._steady_graph().replay()
+                self.launches += self._launches_per_graph
+            rec = self._read_result()
+            self.last_records.append(rec)
+            out.extend(rec.hits)
+            done = rec.done
+            step += 1
+            if step > max_new_tokens + self.N + 4:
+                raise LadeError("decode loop did not terminate (device state corrupt?)")
+        self.last_steps = step
+        return out[:max_length]                                   # lade/decoding.py:1221-1225

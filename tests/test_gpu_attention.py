@@ -1,0 +1,146 @@
+"""Lookahead attention kernel vs (a) the reference module's own output captured in tests/golden and
+(b) the oracle's restatement of the reference eager attention on seeded inputs.
+
+Tolerance (bf16 outputs, |o| <~ 1): the kernel keeps the reference's rounding points for the scores but
+uses online softmax (probabilities are rounded to bf16 before normalisation instead of after), so it is
+not bit-identical: max abs error <= 2e-2 and mean abs error <= 2e-3 are required."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLD, rows_to_bool
+from oracle import llama_ref as LR
+from oracle import lookahead as LA
+
+pytestmark = pytest.mark.gpu
+ATOL_MAX, ATOL_MEAN = 2e-2, 2e-3
+IMPLS = [1]
+
+
+def run_kernel(q, k, v, rowdesc, meta_vals, q_pad, n_splits, impl, kv_capacity=None):
+    """q [Hq, q_len, D], k/v [Hkv, T, D] (cache incl. step rows). Returns [q_len, Hq*D]."""
+    from lookaheaddecoding_b200 import _cabi
+    lib = _cabi.load()
+    Hq, q_len, D = q.shape
+    Hkv, T, _ = k.shape
+    cap = kv_capacity or (T + 70)
+    dev = "cuda"
+    qb = torch.zeros(Hq, q_pad, D, dtype=torch.bfloat16, device=dev)
+    qb[:, :q_len] = q
+    kc = torch.full((Hkv, cap, D), float("nan"), dtype=torch.bfloat16, device=dev)   # stale rows must never leak
+    vc = torch.full((Hkv, cap, D), float("nan"), dtype=torch.bfloat16, device=dev)
+    kc[:, :T], vc[:, :T] = k, v
+    out = torch.zeros(q_pad, Hq * D, dtype=torch.bfloat16, device=dev)
+    meta = torch.zeros(_cabi.META_INTS, dtype=torch.int32, device=dev)
+    for key, val in meta_vals.items():
+        meta[key] = val
+    rd_np = np.full(q_pad, 3 << 30, dtype=np.int64)
+    rd_np[:q_len] = np.asarray(rowdesc, dtype=np.int64)
+    rd = torch.from_numpy(rd_np.astype(np.uint32).view(np.int32)).to(dev)
+    nbytes = lib.lade_attn_scratch_bytes(q_pad, Hq, D, n_splits)
+    scratch = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    _cabi.check(lib.lade_attn_fwd(torch.cuda.current_stream().cuda_stream, qb.data_ptr(), kc.data_ptr(), vc.data_ptr(),
+                                  out.data_ptr(), rd.data_ptr(), meta.data_ptr(), scratch.data_ptr(), q_pad, Hq, Hkv, D,
+                                  cap, T, n_splits, impl), "lade_attn_fwd")
+    torch.cuda.synchronize()
+    assert int(scratch[:65536].view(torch.int32).abs().sum()) == 0, "split counters must self-reset"
+    return out[:q_len]
+
+
+def layout_rowdesc(lay):
+    return [(int(t) << 30) | (int(b) << 15) | int(i & 0x7FFF) for t, b, i in zip(lay.row_type, lay.row_blk, lay.row_idx)]
+
+
+def meta_for(lay, kv_len, q_pad):
+    from lookaheaddecoding_b200 import _cabi as c
+    return {c.M_Q_LEN: lay.q_len, c.M_KV_LEN: kv_len, c.M_N_INPUT: lay.n_input, c.M_LEVEL_OFFSET: lay.level_offset,
+            c.M_ALL_OFFSET: lay.level_offset + lay.dist_offset, c.M_TINY: lay.tiny, c.M_N_LEVELS: len(lay.level_sizes),
+            c.M_N_GUESS_TOK: lay.n_guess_tok, c.M_IS_PREFILL: int(lay.is_prefill), c.M_Q_PAD: q_pad}
+
+
+def check_close(got, want):
+    err = (got.float() - want.float()).abs()
+    assert torch.isfinite(got.float()).all()
+    assert err.max().item() <= ATOL_MAX, f"max abs err {err.max().item():.4g}"
+    assert err.mean().item() <= ATOL_MEAN, f"mean abs err {err.mean().item():.4g}"
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("name", ["attn_tiny_bf16_w15n5g15_pool", "attn_gqa_bf16_w15n5g15", "attn_tiny_bf16_w5n3g3"])
+def test_attention_vs_reference_module_output(name, impl):
+    """Golden q/k/v/o captured from the unmodified reference's LlamaAttention.forward (CPU bf16)."""
+    fx = torch.load(os.path.join(GOLD, name + ".pt"))
+    case = __import__("helpers").load_cases()[fx["case"]]
+    st = case["steps"][fx["step"]]
+    n_in = 1
+    gt = st["guess_tokens"] or []
+    level_sizes = [len(x) for x in st["past_tokens"][: st["fill_level"] + 1]]
+    lay = LA.layout_from_shape(level_sizes, n_in, len(gt), case["N"] - 1)
+    kv_len = fx["kv_len"]
+    np.testing.assert_array_equal(LA.step_mask(lay), rows_to_bool(fx["mask_rows"])[:, kv_len:])
+    q_pad = lay.q_len + 5
+    for n_splits in (1, 3):
+        out = run_kernel(fx["q"].cuda(), fx["k"].cuda(), fx["v"].cuda(), layout_rowdesc(lay), meta_for(lay, kv_len, q_pad),
+                         q_pad, n_splits, impl)
+        check_close(out.cpu(), fx["o"])
+
+
+def _oracle_attn(q, k, v, lay, kv_len):
+    vis = torch.from_numpy(LA.step_mask(lay)).cuda()
+    mask = LR.additive_mask(vis, kv_len, torch.bfloat16)
+    o = LR.eager_attention(q, k, v, mask, q.shape[0] // k.shape[0])
+    return o.transpose(0, 1).reshape(q.shape[1], -1)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("kv_len,W,N,g,Hq,Hkv,splits", [
+    (0, 15, 5, 15, 2, 2, 1), (1, 15, 5, 15, 2, 2, 2), (63, 15, 5, 3, 4, 2, 2), (64, 15, 5, 15, 2, 2, 5),
+    (1000, 15, 5, 15, 8, 8, 5), (3001, 15, 5, 0, 4, 4, 7), (517, 20, 7, 20, 4, 4, 3), (200, 5, 3, 3, 2, 1, 4),
+    (130, 60, 8, 7, 2, 2, 2),
+])
+def test_attention_steady_shapes_vs_oracle(kv_len, W, N, g, Hq, Hkv, splits, impl):
+    torch.manual_seed(kv_len + W)
+    gs = N - 1
+    lay = LA.layout_from_shape([W - 1] + [W] * (N - 2), 1, g * gs, gs)
+    q_len, D = lay.q_len, 128
+    T = kv_len + q_len
+    q = torch.randn(Hq, q_len, D, device="cuda").to(torch.bfloat16)
+    k = torch.randn(Hkv, T, D, device="cuda").to(torch.bfloat16)
+    v = torch.randn(Hkv, T, D, device="cuda").to(torch.bfloat16)
+    q_pad = gs * (W + max(g, 1)) + 4
+    out = run_kernel(q, k, v, layout_rowdesc(lay), meta_for(lay, kv_len, q_pad), q_pad, splits, impl)
+    check_close(out, _oracle_attn(q, k, v, lay, kv_len))
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("P,Hq,Hkv,splits", [(17, 2, 2, 1), (300, 2, 2, 3), (1041, 4, 2, 5)])
+def test_attention_prefill_causal_vs_oracle(P, Hq, Hkv, splits, impl):
+    torch.manual_seed(P)
+    lay = LA.layout_from_shape([P - 1], 1, 0, 4, is_prefill=True)
+    D = 128
+    q = torch.randn(Hq, P, D, device="cuda").to(torch.bfloat16)
+    k = torch.randn(Hkv, P, D, device="cuda").to(torch.bfloat16)
+    v = torch.randn(Hkv, P, D, device="cuda").to(torch.bfloat16)
+    out = run_kernel(q, k, v, layout_rowdesc(lay), meta_for(lay, 0, P), P, splits, impl)
+    check_close(out, _oracle_attn(q, k, v, lay, 0))
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_attention_lp_shapes_vs_oracle(impl):
+    """Lookahead-parallel shapes: re-fed tokens (level_offset) + foreign L0 prefix (dist_offset)."""
+    torch.manual_seed(5)
+    W, N, D_workers, skip, g = 15, 5, 4, 2, 2
+    gs = N - 1
+    split = (W + D_workers - 1) // D_workers
+    for r in range(D_workers):
+        ws, we = min(split * r, W), min(split * (r + 1), W)
+        lay = LA.layout_from_shape([we - 1] + [we - ws] * (N - 2), 1 + skip, g * gs, gs)
+        kv_len, Hq = 77, 2
+        T = kv_len + lay.q_len
+        q = torch.randn(Hq, lay.q_len, 128, device="cuda").to(torch.bfloat16)
+        k = torch.randn(Hq, T, 128, device="cuda").to(torch.bfloat16)
+        v = torch.randn(Hq, T, 128, device="cuda").to(torch.bfloat16)
+        out = run_kernel(q, k, v, layout_rowdesc(lay), meta_for(lay, kv_len, lay.q_len), lay.q_len, 2, impl)
+        check_close(out, _oracle_attn(q, k, v, lay, kv_len))
