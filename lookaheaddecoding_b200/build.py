@@ -19,7 +19,7 @@ STAMP = os.path.join(LIB_DIR, "liblade_sm100.stamp")
 SOURCES = ["state.cu", "layer_ops.cu", "attn_mma.cu", "attn_tc.cu", "attn_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC", "-lcuda",
+    "-shared", "-Xcompiler", "-fPIC",
 ]
 
 

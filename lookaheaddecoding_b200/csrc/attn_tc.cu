@@ -1,8 +1,528 @@
-// Lookahead attention, tcgen05 + TMA path (impl=2).  Placeholder until the kernel lands: fails loudly.
+// Lookahead attention, Blackwell-native path (impl=2): TMA-staged K/V tiles, tcgen05.mma with TMEM
+// accumulators, one softmax thread per query row, split-KV with an in-kernel combine.
+//
+// Per CTA: one (head, 128-row query tile, KV split).  Warp roles (192 threads):
+//   warp 0      TMA producer   Q tile + a STAGES-deep ring of K/V tiles (128 kv rows x 128 d, SWIZZLE_128B)
+//   warp 1      MMA issuer     S = Q K^T  (kind::f16, M=128 N=128 K=16 x8, both operands K-major)
+//                              O += P V   (A = P K-major from smem, B = V MN-major from smem), TMEM alloc
+//   warps 2..5  softmax        tcgen05.ld S row -> reference rounding -> lookahead mask in registers ->
+//                              exp2 -> P (bf16, swizzled into the K tile's smem) ; lazy O rescale in TMEM
+// TMEM: S double buffer (2 x 128 cols) + O (128 cols).
+//
+// Numerics follow attn_mma.cu / the reference (lade/models/modeling_llama.py:520-541); the mask is the
+// same register predicate (common.cuh row_sees == modeling_llama.py:115-207).
 #include "common.cuh"
+
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
 namespace lade {
-int attn_fwd_tc_launch(cudaStream_t, const void*, const void*, const void*, void*, const int32_t*, const int32_t*,
-                       void*, int, int, int, int, int, int, int) {
-  return LADE_EUNSUPPORTED;
+
+constexpr int TC_BM = 128;
+constexpr int TC_BN = 128;
+constexpr int TC_D = 128;
+constexpr int TC_STAGES = 3;
+constexpr int TC_THREADS = 192;
+constexpr int TC_TILE_BYTES = 128 * 128 * 2;   // one [128 x 128] bf16 tile = two [128 x 64] swizzle blocks
+constexpr int TC_HALF_BYTES = TC_TILE_BYTES / 2;
+constexpr int TC_RD_SMEM = 512;
+constexpr int TC_MAX_COUNTERS = 16384;
+constexpr int TC_SMEM_TILES = TC_TILE_BYTES * (1 + 2 * TC_STAGES);
+constexpr int TC_SMEM_BYTES = TC_SMEM_TILES + 256 + TC_RD_SMEM * 4;
+constexpr float TC_LOG2E = 1.4426950408889634f;
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor, version 1, SWIZZLE_128B):
+//   bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): f32 accumulate, bf16 x bf16, M=128, N=128.
+__host__ __device__ constexpr uint32_t umma_idesc(bool b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+__device__ __forceinline__ unsigned pack2_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<unsigned*>(&v);
+}
+
+// ---- kernel ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out,
+                   const int* __restrict__ rowdesc, const int* __restrict__ meta, float* __restrict__ part_o,
+                   float* __restrict__ part_ml, int* __restrict__ counters, int q_pad, int n_heads, int n_kv_heads,
+                   int n_splits, float inv_sqrt_d) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int split = blockIdx.x, h = blockIdx.y, mt = blockIdx.z;
+  const int q_tiles = gridDim.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int q_len = meta[LADE_M_Q_LEN];
+  const int kv_len = meta[LADE_M_KV_LEN];
+  const int is_prefill = meta[LADE_M_IS_PREFILL];
+  const int level_offset = meta[LADE_M_LEVEL_OFFSET];
+  const int T = kv_len + q_len;
+  int Tm = T;
+  if (is_prefill) Tm = min(T, kv_len + min(q_len, (mt + 1) * TC_BM));
+  const int n_tiles = (Tm + TC_BN - 1) / TC_BN;
+  const int tps = (n_tiles + n_splits - 1) / n_splits;
+  const int n_active = (n_tiles + tps - 1) / tps;
+  if (split >= n_active) return;
+  const int tile_lo = split * tps;
+  const int my_tiles = min(n_tiles, tile_lo + tps) - tile_lo;
+  const int hk = h / (n_heads / n_kv_heads);
+
+  unsigned char* sQ = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_SMEM_TILES);
+  // barrier slots: 0 q_full | 1.. k_full[S] | v_full[S] | stage_free[S] | s_full[2] | p_full[2] | o_final
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const int B_QFULL = 0, B_KFULL = 1, B_VFULL = 1 + TC_STAGES, B_FREE = 1 + 2 * TC_STAGES,
+            B_SFULL = 1 + 3 * TC_STAGES, B_PFULL = 3 + 3 * TC_STAGES, B_OFINAL = 5 + 3 * TC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  int* s_flag = reinterpret_cast<int*>(bars + 25);
+  int* s_rd = reinterpret_cast<int*>(smem + TC_SMEM_TILES + 256);
+  const uint32_t sQ_a = smem_u32(sQ);
+  auto sK_a = [&](int s) { return sQ_a + (uint32_t)TC_TILE_BYTES * (1 + 2 * s); };
+  auto sV_a = [&](int s) { return sQ_a + (uint32_t)TC_TILE_BYTES * (2 + 2 * s); };
+
+  if (threadIdx.x == 0) {
+    if ((sQ_a & 1023u) != 0) __trap();   // SWIZZLE_128B tiles need 1024-byte alignment
+    mbar_init(BAR(B_QFULL), 1);
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(BAR(B_KFULL + s), 1); mbar_init(BAR(B_VFULL + s), 1); mbar_init(BAR(B_FREE + s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(BAR(B_SFULL + b), 1); mbar_init(BAR(B_PFULL + b), 128); }
+    mbar_init(BAR(B_OFINAL), 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  const bool rd_in_smem = (!is_prefill) && q_len <= TC_RD_SMEM;
+  if (rd_in_smem && warp >= 2)
+    for (int i = threadIdx.x - 64; i < q_len; i += 128) s_rd[i] = rowdesc[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_O = tmem_base + 256;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      mbar_expect_tx(BAR(B_QFULL), TC_TILE_BYTES);
+      tma_load_3d(sQ_a, &tmQ, BAR(B_QFULL), 0, mt * TC_BM, h);
+      tma_load_3d(sQ_a + TC_HALF_BYTES, &tmQ, BAR(B_QFULL), 64, mt * TC_BM, h);
+      for (int j = 0; j < my_tiles; ++j) {
+        const int s = j % TC_STAGES;
+        if (j >= TC_STAGES) mbar_wait(BAR(B_FREE + s), ((j / TC_STAGES) - 1) & 1);
+        const int row0 = (tile_lo + j) * TC_BN;
+        mbar_expect_tx(BAR(B_KFULL + s), TC_TILE_BYTES);
+        tma_load_3d(sK_a(s), &tmK, BAR(B_KFULL + s), 0, row0, hk);
+        tma_load_3d(sK_a(s) + TC_HALF_BYTES, &tmK, BAR(B_KFULL + s), 64, row0, hk);
+        mbar_expect_tx(BAR(B_VFULL + s), TC_TILE_BYTES);
+        tma_load_3d(sV_a(s), &tmV, BAR(B_VFULL + s), 0, row0, hk);
+        tma_load_3d(sV_a(s) + TC_HALF_BYTES, &tmV, BAR(B_VFULL + s), 64, row0, hk);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      constexpr uint32_t IDESC_QK = umma_idesc(false);
+      constexpr uint32_t IDESC_PV = umma_idesc(true);
+      auto issue_qk = [&](int j) {
+        const int s = j % TC_STAGES;
+        mbar_wait(BAR(B_KFULL + s), (j / TC_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(j & 1) * 128u;
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = umma_desc(sQ_a + kb * TC_HALF_BYTES + k * 32, 16, 1024);
+            const uint64_t db = umma_desc(sK_a(s) + kb * TC_HALF_BYTES + k * 32, 16, 1024);
+            umma_bf16(d, da, db, IDESC_QK, (kb | k) ? 1u : 0u);
+          }
+        umma_commit(BAR(B_SFULL + (j & 1)));
+      };
+      mbar_wait(BAR(B_QFULL), 0);
+      issue_qk(0);
+      for (int j = 0; j < my_tiles; ++j) {
+        if (j + 1 < my_tiles) issue_qk(j + 1);
+        const int s = j % TC_STAGES;
+        mbar_wait(BAR(B_PFULL + (j & 1)), (j >> 1) & 1);
+        mbar_wait(BAR(B_VFULL + s), (j / TC_STAGES) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          // A = P tile (K-major, lives in the K stage), B = V tile (MN-major: LBO = next 64-wide d block)
+          const uint64_t da = umma_desc(sK_a(s) + (kk >> 2) * TC_HALF_BYTES + (kk & 3) * 32, 16, 1024);
+          const uint64_t db = umma_desc(sV_a(s) + kk * 2048, TC_HALF_BYTES, 1024);
+          umma_bf16(tmem_O, da, db, IDESC_PV, (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(BAR(B_FREE + s));
+        if (j == my_tiles - 1) umma_commit(BAR(B_OFINAL));
+      }
+    }
+  } else {
+    // ================= softmax: one thread per query row =================
+    const int quad = warp & 3;
+    const int row_l = quad * 32 + lane;             // TMEM lane == row inside the tile
+    const int row = mt * TC_BM + row_l;             // step-local row
+    const int rd_r = row < q_pad ? rowdesc[row] : rowdesc_make(LADE_ROW_PAD, 0, 0);
+    const int* rdp = rd_in_smem ? s_rd : rowdesc;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    float m_used = -INFINITY, l_sum = 0.f;
+    float sv[128];
+    for (int j = 0; j < my_tiles; ++j) {
+      const int buf = j & 1, s = j % TC_STAGES;
+      mbar_wait(BAR(B_SFULL + buf), (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t ts = tmem_base + lane_addr + (uint32_t)buf * 128u;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(ts + c * 32, sv + c * 32);
+      tmem_ld_wait();
+      const int col0 = (tile_lo + j) * TC_BN;
+      const bool need_mask = (col0 + TC_BN > kv_len);
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 128; ++i) {
+        float x = bf16_round(bf16_round(sv[i]) * inv_sqrt_d);
+        if (need_mask) {
+          const int col = col0 + i;
+          bool vis;
+          if (col < kv_len) vis = true;
+          else if (col >= T) vis = false;
+          else {
+            const int c = col - kv_len;
+            if (is_prefill) vis = (row < q_len) ? (c <= row) : (c == row);
+            else vis = row_sees(rd_r, row, rdp[c], c, level_offset);
+          }
+          if (!vis) x = -INFINITY;
+        }
+        sv[i] = x;
+        mx = fmaxf(mx, x);
+      }
+      // lazy rescale: keep the stale max while it is within 2^8 of the running max
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        const bool need = (mx > m_used + 5.545177f) || (m_used == -INFINITY && mx > -INFINITY);
+        if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(BAR(B_FREE + (j - 1) % TC_STAGES), ((j - 1) / TC_STAGES) & 1);   // PV(j-1) landed in O
+          tc_fence_after();
+          const float m_new = fmaxf(m_used, mx);
+          const float scale = (m_new == -INFINITY) ? 1.f : exp2f((m_used - m_new) * TC_LOG2E);
+          l_sum *= scale;
+          float ov[32];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            tmem_ld32(tmem_O + lane_addr + c * 32, ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ov[i] *= scale;
+            tmem_st32(tmem_O + lane_addr + c * 32, ov);
+          }
+          tmem_st_wait();
+          m_used = m_new;
+        }
+      }
+      const float off = (m_used == -INFINITY) ? 0.f : m_used * TC_LOG2E;
+      // P (bf16) into the K stage, K-major SWIZZLE_128B: [kv block of 64][row][128 B], 16 B chunk ^ (row & 7)
+      unsigned char* pK = smem + TC_TILE_BYTES * (1 + 2 * s);
+      float psum = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < 16; ++ch) {
+        float p[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          p[e] = exp2f(sv[ch * 8 + e] * TC_LOG2E - off);
+          psum += p[e];
+        }
+        uint4 pk;
+        pk.x = pack2_bf16(p[0], p[1]); pk.y = pack2_bf16(p[2], p[3]);
+        pk.z = pack2_bf16(p[4], p[5]); pk.w = pack2_bf16(p[6], p[7]);
+        const int kb = ch >> 3, cc = ch & 7;
+        *reinterpret_cast<uint4*>(pK + kb * TC_HALF_BYTES + row_l * 128 + ((cc ^ (row_l & 7)) << 4)) = pk;
+      }
+      l_sum += psum;
+      // stale cache rows past T must not reach the PV MMA (0 * NaN): zero them in the staged V tile
+      if (col0 + TC_BN > T) {
+        mbar_wait(BAR(B_VFULL + s), (j / TC_STAGES) & 1);
+        if (col0 + row_l >= T) {
+          unsigned char* pV = smem + TC_TILE_BYTES * (2 + 2 * s);
+          const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) {
+            *reinterpret_cast<uint4*>(pV + row_l * 128 + cc * 16) = z;
+            *reinterpret_cast<uint4*>(pV + TC_HALF_BYTES + row_l * 128 + cc * 16) = z;
+          }
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(BAR(B_PFULL + buf));
+    }
+
+    // ---- epilogue: O (TMEM) -> final output or split partial
+    mbar_wait(BAR(B_OFINAL), 0);
+    tc_fence_after();
+    const int HD = n_heads * TC_D;
+    const long long rows_pad = (long long)q_tiles * TC_BM;
+    if (n_active == 1) {
+      const float inv = l_sum > 0.f ? 1.f / l_sum : 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float ov[32];
+        tmem_ld32(tmem_O + lane_addr + c * 32, ov);
+        tmem_ld_wait();
+        if (row < q_pad) {
+          uint4* dst = reinterpret_cast<uint4*>(out + (long long)row * HD + h * TC_D + c * 32);
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            uint4 pk;
+            pk.x = pack2_bf16(ov[v4 * 8 + 0] * inv, ov[v4 * 8 + 1] * inv);
+            pk.y = pack2_bf16(ov[v4 * 8 + 2] * inv, ov[v4 * 8 + 3] * inv);
+            pk.z = pack2_bf16(ov[v4 * 8 + 4] * inv, ov[v4 * 8 + 5] * inv);
+            pk.w = pack2_bf16(ov[v4 * 8 + 6] * inv, ov[v4 * 8 + 7] * inv);
+            dst[v4] = pk;
+          }
+        }
+      }
+    } else {
+      float* po = part_o + (((long long)split * n_heads + h) * rows_pad + row) * TC_D;
+      float* pml = part_ml + (((long long)split * n_heads + h) * rows_pad + row) * 2;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float ov[32];
+        tmem_ld32(tmem_O + lane_addr + c * 32, ov);
+        tmem_ld_wait();
+#pragma unroll
+        for (int v4 = 0; v4 < 8; ++v4)
+          reinterpret_cast<float4*>(po + c * 32)[v4] = make_float4(ov[v4 * 4], ov[v4 * 4 + 1], ov[v4 * 4 + 2], ov[v4 * 4 + 3]);
+      }
+      *reinterpret_cast<float2*>(pml) = make_float2(m_used, l_sum);
+    }
+    tc_fence_before();
+  }
+
+  // ---- teardown + split combine (last CTA of this (head, q tile))
+  __threadfence();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+  if (n_active == 1) return;
+  if (threadIdx.x == 0) {
+    const int prev = atomicAdd(&counters[h * q_tiles + mt], 1);
+    *s_flag = (prev == n_active - 1);
+  }
+  __syncthreads();
+  if (!*s_flag) return;
+  __threadfence();
+  const int HD = n_heads * TC_D;
+  const long long rows_pad = (long long)q_tiles * TC_BM;
+  for (int idx = threadIdx.x; idx < TC_BM * (TC_D / 4); idx += TC_THREADS) {
+    const int rl = idx / (TC_D / 4), c4 = idx % (TC_D / 4);
+    const int row = mt * TC_BM + rl;
+    if (row >= q_pad) continue;
+    float mmax = -INFINITY;
+    for (int s = 0; s < n_active; ++s)
+      mmax = fmaxf(mmax, __ldcg(part_ml + ((((long long)s * n_heads + h) * rows_pad) + row) * 2));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float lsum = 0.f;
+    for (int s = 0; s < n_active; ++s) {
+      const float2 ml = __ldcg(reinterpret_cast<const float2*>(part_ml + ((((long long)s * n_heads + h) * rows_pad) + row) * 2));
+      const float wgt = (ml.x == -INFINITY) ? 0.f : exp2f((ml.x - mmax) * TC_LOG2E);
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(part_o + ((((long long)s * n_heads + h) * rows_pad) + row) * TC_D + c4 * 4));
+      acc.x += v.x * wgt; acc.y += v.y * wgt; acc.z += v.z * wgt; acc.w += v.w * wgt;
+      lsum += ml.y * wgt;
+    }
+    const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
+    uint2 pk;
+    pk.x = pack2_bf16(acc.x * inv, acc.y * inv);
+    pk.y = pack2_bf16(acc.z * inv, acc.w * inv);
+    *reinterpret_cast<uint2*>(out + (long long)row * HD + h * TC_D + c4 * 4) = pk;
+  }
+  if (threadIdx.x == 0) counters[h * q_tiles + mt] = 0;
+}
+
+// ---- host: tensor maps ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; int rows; int heads;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && heads == o.heads; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    return std::hash<const void*>()(k.ptr) ^ (std::hash<int>()(k.rows) * 31) ^ (std::hash<int>()(k.heads) * 131);
+  }
+};
+
+// [heads][rows][128] bf16, box = 64 d x 128 rows x 1 head, SWIZZLE_128B; out-of-range rows are zero filled
+static int get_tensor_map(const void* ptr, int rows, int heads, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  MapKey key{ptr, rows, heads};
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return LADE_OK; }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return LADE_EUNSUPPORTED;
+  CUtensorMap tm;
+  const cuuint64_t dims[3] = {(cuuint64_t)TC_D, (cuuint64_t)rows, (cuuint64_t)heads};
+  const cuuint64_t strides[2] = {(cuuint64_t)TC_D * 2, (cuuint64_t)rows * TC_D * 2};
+  const cuuint32_t box[3] = {64, 128, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return LADE_ECUDA;
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, tm);
+  *out = tm;
+  return LADE_OK;
+}
+
+int attn_fwd_tc_launch(cudaStream_t stream, const void* q, const void* k_cache, const void* v_cache, void* out,
+                       const int32_t* rowdesc, const int32_t* meta, void* scratch, int q_pad, int n_heads,
+                       int n_kv_heads, int head_dim, int kv_capacity, int kv_bound, int n_splits) {
+  (void)kv_bound;
+  if (head_dim != TC_D) return LADE_EUNSUPPORTED;
+  const int q_tiles = (q_pad + TC_BM - 1) / TC_BM;
+  if ((long long)n_heads * q_tiles > TC_MAX_COUNTERS) return LADE_EUNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(k_cache) & 15) ||
+      (reinterpret_cast<uintptr_t>(v_cache) & 15))
+    return LADE_EINVAL;
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  if ((rc = get_tensor_map(q, q_pad, n_heads, &tmQ)) != LADE_OK) return rc;
+  if ((rc = get_tensor_map(k_cache, kv_capacity, n_kv_heads, &tmK)) != LADE_OK) return rc;
+  if ((rc = get_tensor_map(v_cache, kv_capacity, n_kv_heads, &tmV)) != LADE_OK) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LADE_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  const long long rows_pad = (long long)q_tiles * TC_BM;
+  int* counters = reinterpret_cast<int*>(scratch);
+  float* part_ml = reinterpret_cast<float*>(counters + TC_MAX_COUNTERS);
+  float* part_o = part_ml + (long long)n_splits * n_heads * rows_pad * 2;
+  dim3 grid(n_splits, n_heads, q_tiles);
+  attn_fwd_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(
+      tmQ, tmK, tmV, (__nv_bfloat16*)out, rowdesc, meta, part_o, part_ml, counters, q_pad, n_heads, n_kv_heads, n_splits,
+      1.0f / sqrtf((float)head_dim));
+  LADE_LAUNCH_CHECK("attn_fwd_tc_kernel");
+  return LADE_OK;
+}
+
 }  // namespace lade

@@ -16,7 +16,7 @@ from oracle import lookahead as LA
 
 pytestmark = pytest.mark.gpu
 ATOL_MAX, ATOL_MEAN = 2e-2, 2e-3
-IMPLS = [1]
+IMPLS = [int(x) for x in os.environ.get("LADE_TEST_ATTN_IMPLS", "1").split(",")]
 
 
 def run_kernel(q, k, v, rowdesc, meta_vals, q_pad, n_splits, impl, kv_capacity=None):
