@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--attn-splits", type=int, default=0)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-profiler-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed region (use with ncu --profile-from-start off)")
     return ap.parse_args()
 
 
@@ -154,16 +156,33 @@ def attn_roofline(eng, shape, reps=5):
     from lookaheaddecoding_b200 import _cabi
 
     lib = eng.lib
-    meta = eng.meta.cpu().tolist()
-    q_len, kv_len = meta[_cabi.M_Q_LEN], meta[_cabi.M_KV_LEN]
+    meta_now = eng.meta.cpu().tolist()
+    kv_len = meta_now[_cabi.M_KV_LEN]
     rows = eng.q_steady
+    # full steady-state layout of the metric's shape (q = (N-1)(W+G) rows: every guess slot filled); random-init
+    # weights on a random prompt rarely produce pool hits, so the live decode mostly runs with fewer rows
+    W, N, G, GS = eng.W, eng.N, eng.G, eng.GS
+    q_len = GS * (W + G)
+    rd = []
+    for r in range(q_len):
+        if r < (N - 1) * W:
+            rd.append((1 << 30) | ((r // W) << 15) | (r % W))            # WINDOW(level, column); a_off = 0
+        else:
+            g = r - (N - 1) * W
+            rd.append((2 << 30) | ((g // GS) << 15) | (g % GS))          # GUESS(n-gram, index)
+    import numpy as np
+    rowdesc = torch.from_numpy(np.asarray(rd, dtype=np.uint32).view(np.int32)).to(eng.dev)
+    meta = torch.zeros(_cabi.META_INTS, dtype=torch.int32, device=eng.dev)
+    for k, v in {_cabi.M_Q_LEN: q_len, _cabi.M_KV_LEN: kv_len, _cabi.M_N_INPUT: 1, _cabi.M_TINY: W,
+                 _cabi.M_N_LEVELS: N - 1, _cabi.M_N_GUESS_TOK: G * GS, _cabi.M_PHASE: 2, _cabi.M_Q_PAD: rows}.items():
+        meta[k] = v
     qb = eng.qb if rows == eng.rows_cap else eng.qb.view(-1)[: eng.nh * rows * eng.D].view(eng.nh, rows, eng.D)
     stream = torch.cuda.current_stream(eng.dev)
 
     def one_pass():
         for l in range(eng.L):
             _cabi.check(lib.lade_attn_fwd(stream.cuda_stream, qb.data_ptr(), eng.kv[l, 0].data_ptr(), eng.kv[l, 1].data_ptr(),
-                                          eng.attn_out.data_ptr(), eng.rowdesc.data_ptr(), eng.meta.data_ptr(),
+                                          eng.attn_out.data_ptr(), rowdesc.data_ptr(), meta.data_ptr(),
                                           eng.attn_scratch.data_ptr(), rows, eng.nh, eng.nkv, eng.D, eng.kv_capacity,
                                           eng.kv_capacity, eng.attn_splits, eng.attn_impl))
     for _ in range(3):
@@ -293,6 +312,8 @@ def main():
     launches0 = eng.launches
     with sampler:
         barrier()
+        if args.cuda_profiler_range:
+            torch.cuda.profiler.start()
         e0.record()
         for _ in range(args.steps):
             out = eng.generate(prompt_list, args.max_new, rng=random.Random(0))
@@ -300,6 +321,8 @@ def main():
             steps += eng.last_steps
         e1.record()
         barrier()
+        if args.cuda_profiler_range:
+            torch.cuda.profiler.stop()
         dev_ms = e0.elapsed_time(e1)
         launches = eng.launches - launches0
         # ---- end to end through the plugin surface: pinned host prompt -> generate() -> host ids

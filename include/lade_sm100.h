@@ -157,7 +157,7 @@ int lade_attn_fwd(void* stream, const void* q, const void* k_cache, const void* 
                   const int32_t* rowdesc, const int32_t* meta, void* scratch, int32_t q_pad,
                   int32_t n_heads, int32_t n_kv_heads, int32_t head_dim, int32_t kv_capacity,
                   int32_t kv_bound /* host upper bound of kv_len + q_len */, int32_t n_splits,
-                  int32_t impl /* 0 = default, 1 = mma.sync path, 2 = tcgen05 path */);
+                  int32_t impl /* 0 = default (= 2), 1 = mma.sync path, 2 = tcgen05/TMA path */);
 int64_t lade_attn_scratch_bytes(int32_t q_pad, int32_t n_heads, int32_t head_dim, int32_t n_splits);
 
 /* act = bf16(silu(gate)) * up on the fused [rows][2*inter] projection.  LlamaMLP, modeling_llama.py:378. */
@@ -189,9 +189,21 @@ int lade_ctx_output_ids(LadeCtx* ctx, void* stream, int32_t* out_host, int32_t n
 int lade_ctx_pool_snapshot(LadeCtx* ctx, void* stream, int32_t* cnt_host, int32_t* tup_host);
 int lade_ctx_window_snapshot(LadeCtx* ctx, void* stream, int32_t* win_host, int32_t* len_host);
 
-/* ---- lookahead parallelism (lade_distributed; lade/decoding.py:956-984,1088-1107) --------------- */
-/* LP record of one rank for one step: [max_hit, hits[N-1], n_new, new_results slice...]. */
+/* ---- lookahead parallelism (lade_distributed; lade/decoding.py:905-906,956-984,1023-1107,1148-1153) ---
+ * Every rank holds a model replica and the same window + pool; rank r evaluates window columns
+ * [ws, we) and its share of the candidate n-grams (lade_step_layout does the slicing from
+ * LadeConfig.dist_workers / .rank).  Per step each rank writes ONE fixed-size int32 record
+ *   [first_guess, max_hit, n_new, hits[N-1], new_tokens[W+N-3]]
+ * with lade_lp_verify; the caller all-gathers the records (a single ncclAllGather over NVLink, rank order);
+ * lade_lp_commit reduces them identically on every rank (max hit, lowest rank wins ties; window tokens
+ * concatenated in rank order) and applies the state update -- this replaces the pickled object
+ * collectives of decoding.py:1024,1045,1057,1090,1096,1106.  With a hit, no KV is copied: the accepted
+ * tokens are re-fed next step (decoding.py:1148-1153). */
 int lade_lp_record_ints(const LadeConfig* cfg);
+int lade_lp_verify(LadeCtx* ctx, void* stream, const int32_t* argmax_slots, const int32_t* meta,
+                   int32_t* record_out);
+int lade_lp_commit(LadeCtx* ctx, void* stream, const int32_t* records_all /* [D][record_ints] */,
+                   const int32_t* meta, int32_t* result);
 
 const char* lade_strerror(int code);
 const char* lade_last_cuda_error(void);

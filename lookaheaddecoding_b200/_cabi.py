@@ -53,6 +53,8 @@ _SIGNATURES = {
     "lade_ctx_pool_snapshot": (C.c_int, [c_p, c_p, c_p, c_p]),
     "lade_ctx_window_snapshot": (C.c_int, [c_p, c_p, c_p, c_p]),
     "lade_lp_record_ints": (C.c_int, [C.POINTER(LadeConfig)]),
+    "lade_lp_verify": (C.c_int, [c_p, c_p, c_p, c_p, c_p]),
+    "lade_lp_commit": (C.c_int, [c_p, c_p, c_p, c_p, c_p]),
     "lade_strerror": (C.c_char_p, [C.c_int]),
     "lade_last_cuda_error": (C.c_char_p, []),
     "lade_version": (C.c_int, []),

@@ -25,7 +25,7 @@ int lade_attn_fwd(void* stream, const void* q, const void* k_cache, const void* 
   if (!q || !k_cache || !v_cache || !out || !rowdesc || !meta || !scratch) return LADE_EINVAL;
   if (q_pad < 1 || n_heads < 1 || n_kv_heads < 1 || n_heads % n_kv_heads != 0 || n_splits < 1 || kv_capacity < 1)
     return LADE_EINVAL;
-  if (impl == 2)
+  if (impl == 0 || impl == 2)   // default: the Blackwell-native tcgen05/TMA kernel
     return lade::attn_fwd_tc_launch((cudaStream_t)stream, q, k_cache, v_cache, out, rowdesc, meta, scratch, q_pad,
                                     n_heads, n_kv_heads, head_dim, kv_capacity, kv_bound, n_splits);
   return lade::attn_fwd_mma_launch((cudaStream_t)stream, q, k_cache, v_cache, out, rowdesc, meta, scratch, q_pad,

@@ -73,49 +73,66 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const __nv_bfloat16* __res
   }
 }
 
-// RoPE + append.  grid: (rows, Hq + 2*Hkv) ; block: D/2 threads (one rotation pair each, D <= 256).
-__global__ void rope_append_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ cos_tab,
-                                   const __nv_bfloat16* __restrict__ sin_tab, const int* __restrict__ pos,
-                                   const int* __restrict__ meta, __nv_bfloat16* __restrict__ q_out,
-                                   __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache,
-                                   int q_pad, int n_heads, int n_kv_heads, int D, int kv_capacity, int max_pos) {
+// RoPE + append.  grid: rows ; block: 256 threads.  Work item = (head, 8-wide slice of the first half):
+// the thread rotates elements [8i, 8i+8) of the first half against the same slice of the second half,
+// all accesses 16 bytes.  (Hq + 2 Hkv) * D/16 items per row.
+__global__ void __launch_bounds__(256) rope_append_kernel(
+    const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ cos_tab,
+    const __nv_bfloat16* __restrict__ sin_tab, const int* __restrict__ pos, const int* __restrict__ meta,
+    __nv_bfloat16* __restrict__ q_out, __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache,
+    int q_pad, int n_heads, int n_kv_heads, int D, int kv_capacity, int max_pos) {
   const int r = blockIdx.x;
-  const int h = blockIdx.y;
-  const int t = threadIdx.x;  // pair index in [0, D/2)
   const int half = D >> 1;
+  const int per_head = half >> 3;                        // 16-byte slices per half head
+  const int n_items = (n_heads + 2 * n_kv_heads) * per_head;
   const int ld = (n_heads + 2 * n_kv_heads) * D;
-  const __nv_bfloat16* src = qkv + (long long)r * ld + (long long)h * D;
   const int kv_len = meta[LADE_M_KV_LEN];
   const int cache_row = kv_len + r;
-  if (h >= n_heads + n_kv_heads) {  // V: plain append
-    const int hv = h - n_heads - n_kv_heads;
-    if (cache_row < kv_capacity) {
-      __nv_bfloat16* dst = v_cache + ((long long)hv * kv_capacity + cache_row) * D;
-      dst[t] = src[t];
-      dst[t + half] = src[t + half];
-    }
-    return;
-  }
   int p = pos[r];
   p = p < 0 ? 0 : (p >= max_pos ? max_pos - 1 : p);
-  const float x1 = __bfloat162float(src[t]);
-  const float x2 = __bfloat162float(src[t + half]);
-  const float c1 = __bfloat162float(cos_tab[(long long)p * D + t]);
-  const float c2 = __bfloat162float(cos_tab[(long long)p * D + t + half]);
-  const float s1 = __bfloat162float(sin_tab[(long long)p * D + t]);
-  const float s2 = __bfloat162float(sin_tab[(long long)p * D + t + half]);
-  // (q * cos) + (rotate_half(q) * sin), every op rounded to bf16 (modeling_llama.py:344-345)
-  const float o1 = bf16_round(bf16_round(x1 * c1) + bf16_round(-x2 * s1));
-  const float o2 = bf16_round(bf16_round(x2 * c2) + bf16_round(x1 * s2));
-  __nv_bfloat16* dst;
-  if (h < n_heads) {
-    dst = q_out + ((long long)h * q_pad + r) * D;
-  } else {
-    if (cache_row >= kv_capacity) return;
-    dst = k_cache + ((long long)(h - n_heads) * kv_capacity + cache_row) * D;
+  const __nv_bfloat16* crow = cos_tab + (long long)p * D;
+  const __nv_bfloat16* srow = sin_tab + (long long)p * D;
+  for (int it = threadIdx.x; it < n_items; it += blockDim.x) {
+    const int h = it / per_head, sl = it % per_head;
+    const __nv_bfloat16* src = qkv + (long long)r * ld + (long long)h * D + sl * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(src);
+    const uint4 b = *reinterpret_cast<const uint4*>(src + half);
+    __nv_bfloat16* dst;
+    if (h < n_heads) {
+      dst = q_out + ((long long)h * q_pad + r) * D + sl * 8;
+    } else if (h < n_heads + n_kv_heads) {
+      if (cache_row >= kv_capacity) continue;
+      dst = k_cache + ((long long)(h - n_heads) * kv_capacity + cache_row) * D + sl * 8;
+    } else {                                              // V: plain append
+      if (cache_row >= kv_capacity) continue;
+      dst = v_cache + ((long long)(h - n_heads - n_kv_heads) * kv_capacity + cache_row) * D + sl * 8;
+      *reinterpret_cast<uint4*>(dst) = a;
+      *reinterpret_cast<uint4*>(dst + half) = b;
+      continue;
+    }
+    const uint4 c1 = *reinterpret_cast<const uint4*>(crow + sl * 8);
+    const uint4 c2 = *reinterpret_cast<const uint4*>(crow + half + sl * 8);
+    const uint4 s1 = *reinterpret_cast<const uint4*>(srow + sl * 8);
+    const uint4 s2 = *reinterpret_cast<const uint4*>(srow + half + sl * 8);
+    const __nv_bfloat16* x1 = reinterpret_cast<const __nv_bfloat16*>(&a);
+    const __nv_bfloat16* x2 = reinterpret_cast<const __nv_bfloat16*>(&b);
+    const __nv_bfloat16* pc1 = reinterpret_cast<const __nv_bfloat16*>(&c1);
+    const __nv_bfloat16* pc2 = reinterpret_cast<const __nv_bfloat16*>(&c2);
+    const __nv_bfloat16* ps1 = reinterpret_cast<const __nv_bfloat16*>(&s1);
+    const __nv_bfloat16* ps2 = reinterpret_cast<const __nv_bfloat16*>(&s2);
+    uint4 o1v, o2v;
+    __nv_bfloat16* o1 = reinterpret_cast<__nv_bfloat16*>(&o1v);
+    __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(&o2v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float f1 = __bfloat162float(x1[j]), f2 = __bfloat162float(x2[j]);
+      // (q * cos) + (rotate_half(q) * sin), every op rounded to bf16 (modeling_llama.py:344-345)
+      o1[j] = __float2bfloat16_rn(bf16_round(f1 * __bfloat162float(pc1[j])) + bf16_round(-f2 * __bfloat162float(ps1[j])));
+      o2[j] = __float2bfloat16_rn(bf16_round(f2 * __bfloat162float(pc2[j])) + bf16_round(f1 * __bfloat162float(ps2[j])));
+    }
+    *reinterpret_cast<uint4*>(dst) = o1v;
+    *reinterpret_cast<uint4*>(dst + half) = o2v;
   }
-  dst[t] = __float2bfloat16_rn(o1);
-  dst[t + half] = __float2bfloat16_rn(o2);
 }
 
 __global__ void swiglu_kernel(const __nv_bfloat16* __restrict__ gate_up, __nv_bfloat16* __restrict__ out,
@@ -181,9 +198,8 @@ int lade_rope_append(void* stream, const void* qkv, const void* cos_tab, const v
                      int32_t rows, int32_t q_pad, int32_t n_heads, int32_t n_kv_heads, int32_t head_dim,
                      int32_t kv_capacity, int32_t max_pos) {
   if (!qkv || !cos_tab || !sin_tab || !pos || !meta || !q_out || !k_cache || !v_cache) return LADE_EINVAL;
-  if (rows < 1 || rows > q_pad || head_dim % 2 != 0 || head_dim > 512 || n_heads < 1 || n_kv_heads < 1) return LADE_EINVAL;
-  dim3 grid(rows, n_heads + 2 * n_kv_heads);
-  rope_append_kernel<<<grid, head_dim / 2, 0, (cudaStream_t)stream>>>(
+  if (rows < 1 || rows > q_pad || head_dim % 16 != 0 || head_dim > 512 || n_heads < 1 || n_kv_heads < 1) return LADE_EINVAL;
+  rope_append_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)cos_tab, (const __nv_bfloat16*)sin_tab, pos, meta,
       (__nv_bfloat16*)q_out, (__nv_bfloat16*)k_cache, (__nv_bfloat16*)v_cache, q_pad, n_heads, n_kv_heads,
       head_dim, kv_capacity, max_pos);

@@ -24,11 +24,12 @@ void set_cuda_error(cudaError_t e, const char* where) {
 // header ints of the device state block
 enum {
   S_FILL_LEVEL = 0, S_LST_TOKEN, S_KV_LEN, S_N_OUT, S_N_OLD, S_DONE, S_STEPS, S_MAX_LENGTH,
-  S_N_PROMPT, S_N_GUESS_TOK, S_HDR_INTS = 16
+  S_N_PROMPT, S_N_GUESS_TOK, S_SKIP, S_HDR_INTS = 16
 };
 
 struct Dims {
   int W, N, G, GS, WCAP, V, cap, pool_from_prompt, n_eos;
+  int D, rank;   // lookahead parallelism: DIST_WORKERS, LOCAL_RANK (1, 0 when off)
   int eos[4];
   int lm_cap;
   // offsets (in ints) into the state block
@@ -119,6 +120,7 @@ __global__ void reset_header_kernel(int* st, Dims d, int n_prompt, int n_window0
     st[S_MAX_LENGTH] = max_length;
     st[S_N_PROMPT] = n_prompt;
     st[S_N_GUESS_TOK] = 0;
+    st[S_SKIP] = 0;
   }
   if (t < d.N - 1) st[d.off_win_len + t] = (t == 0) ? n_window0 : 0;
   // all_old_tokens starts as a copy of the prompt (decoding.py:879)
@@ -130,6 +132,7 @@ __global__ void step_layout_kernel(int* st, Dims d, int q_pad, int* ids_out, int
                                    int* lm_rows, int* meta) {
   __shared__ int s_sizes[64];
   __shared__ int s_start[64];
+  __shared__ int s_off[64];
   __shared__ int s_hdr[16];
   const int t = threadIdx.x;
   const int N = d.N, GS = d.GS;
@@ -138,16 +141,32 @@ __global__ void step_layout_kernel(int* st, Dims d, int q_pad, int* ids_out, int
     const int* wl = st + d.off_win_len;
     int phase = (wl[1] == 0) ? 0 : ((wl[N - 2] == 0) ? 1 : 2);
     const int n_out = st[S_N_OUT];
-    const int n_input = (phase == 0) ? n_out : 1;
+    const int skip = st[S_SKIP];                                                        // decoding.py:941-942
+    const int n_input = (phase == 0) ? n_out : 1 + skip;
+    // lookahead parallelism: this rank owns window columns [ws, we) (decoding.py:973-984)
+    int ws = 0, we = wl[0] + 1;
+    if (d.D > 1) {
+      const int window_len = wl[0] + 1;
+      const int split = (window_len + d.D - 1) / d.D;
+      ws = min(split * d.rank, window_len);
+      we = min(split * (d.rank + 1), window_len);
+    }
     int acc = n_input;
     for (int l = 0; l <= fill; ++l) {
-      s_sizes[l] = wl[l];
+      const int sz = (l == 0) ? max(we - 1, 0) : (d.D > 1 ? we - ws : wl[l]);
+      s_sizes[l] = sz;
+      s_off[l] = (l == 0 || d.D == 1) ? 0 : ws;
       s_start[l] = acc;
-      acc += wl[l];
+      acc += sz;
     }
-    int n_ng = 0;
+    int n_ng = 0, g0 = 0;
     const int lst = st[S_LST_TOKEN];
     if (phase == 2 && lst >= 0 && lst < d.V && d.G > 0) n_ng = st[d.off_cnt + lst];     // decoding.py:948
+    if (d.D > 1 && n_ng > 0) {                                                          // decoding.py:956-963
+      const int per = (n_ng + d.D - 1) / d.D;
+      g0 = min(per * d.rank, n_ng);
+      n_ng = min(per * (d.rank + 1), n_ng) - g0;
+    }
     const int lg = n_ng * GS;
     const int q_len = acc + lg;
     const int tiny = s_sizes[fill];
@@ -156,6 +175,7 @@ __global__ void step_layout_kernel(int* st, Dims d, int q_pad, int* ids_out, int
     s_hdr[0] = phase; s_hdr[1] = n_input; s_hdr[2] = fill + 1; s_hdr[3] = lg; s_hdr[4] = q_len;
     s_hdr[5] = tiny; s_hdr[6] = level_offset; s_hdr[7] = level_offset + dist_offset;
     s_hdr[8] = n_out; s_hdr[9] = lst; s_hdr[10] = acc;  // acc = first guess row
+    s_hdr[11] = g0 * GS;
     st[S_N_GUESS_TOK] = lg;
     meta[LADE_M_Q_LEN] = q_len;
     meta[LADE_M_KV_LEN] = st[S_KV_LEN];
@@ -176,7 +196,7 @@ __global__ void step_layout_kernel(int* st, Dims d, int q_pad, int* ids_out, int
   const int tiny = s_hdr[5], a_off = s_hdr[7], n_out = s_hdr[8], lst = s_hdr[9], g_row0 = s_hdr[10];
   const int lst_id = n_out - 1;                                                         // modeling :1466
   const int* out_ids = st + d.off_out;
-  const int* gsrc = st + d.off_tup + (long long)(lst < 0 ? 0 : lst) * d.G * GS;
+  const int* gsrc = st + d.off_tup + (long long)(lst < 0 ? 0 : lst) * d.G * GS + s_hdr[11];
   int* gdst = st + d.off_guess;
   for (int r = t; r < q_pad; r += blockDim.x) {
     int id = 0, pos = 0, rd = rowdesc_make(LADE_ROW_PAD, 0, 0);
@@ -187,7 +207,7 @@ __global__ void step_layout_kernel(int* st, Dims d, int q_pad, int* ids_out, int
       int l = 0;
       while (l + 1 < n_levels && r >= s_start[l + 1]) ++l;
       const int j = r - s_start[l];
-      id = st_win(st, d, l)[j];
+      id = st_win(st, d, l)[s_off[l] + j];
       if (l == 0) pos = lst_id + 1 + j;                                                 // modeling :1494
       else pos = lst_id + l + (s_sizes[0] + 1 - s_sizes[l]) + j;                        // modeling :1496-1497
     } else if (r < q_len) {
@@ -198,7 +218,7 @@ __global__ void step_layout_kernel(int* st, Dims d, int q_pad, int* ids_out, int
     }
     if (r < q_len) {
       if (phase == 0 || r < a_off) rd = rowdesc_make(LADE_ROW_PREFIX, 0, r & 0x7fff);
-      else if (r < g_row0) rd = rowdesc_make(LADE_ROW_WINDOW, (r - a_off) / tiny, (r - a_off) % tiny);
+      else if (r < g_row0) rd = rowdesc_make(LADE_ROW_WINDOW, (r - a_off) / max(tiny, 1), (r - a_off) % max(tiny, 1));
       else rd = rowdesc_make(LADE_ROW_GUESS, (r - g_row0) / GS, (r - g_row0) % GS);
     }
     ids_out[r] = id;
@@ -220,35 +240,112 @@ __global__ void step_layout_kernel(int* st, Dims d, int q_pad, int* ids_out, int
 }
 
 // ---- verify + accept + pool update ---------------------------------------------------------------
-__global__ void accept_update_kernel(int* st, Dims d, const int* __restrict__ am, const int* __restrict__ meta,
-                                     int* res) {
-  __shared__ int s_key[128];
-  __shared__ int s_hits[64];
-  __shared__ int s_tup[64];
-  __shared__ int s_new[1024];
-  __shared__ int s_best;
+// A step's decision: what every rank must agree on before the state update.  Single GPU: computed and
+// applied by one kernel.  Lookahead parallelism: each rank writes its local decision as a fixed-size
+// int32 record, the records are all-gathered (one NCCL call), every rank reduces them identically.
+//   record = [first_guess, max_hit, n_new, hits[GS], new_tokens[WCAP]]
+struct Decision {
+  int first_guess, max_hit, max_hit_idx, n_new;
+  int hits[64];
+  int new_tok[1024 + 64];
+};
+
+__device__ __forceinline__ int lp_rec_ints(const Dims& d) { return 3 + d.GS + d.WCAP; }
+
+// Local part: argmax slots -> decision (longest-prefix accept over this rank's guesses, decoding.py:1071-1084).
+__device__ void local_decision(int* st, const Dims& d, const int* __restrict__ am, const int* __restrict__ meta,
+                               Decision* dec, int* s_best) {
   const int t = threadIdx.x;
-  const int N = d.N, GS = d.GS, W = d.W, WCAP = d.WCAP;
-  if (st[S_DONE]) {
-    if (t == 0) { res[LADE_R_N_EMIT] = 0; res[LADE_R_DONE] = 1; res[LADE_R_MAX_HIT] = 0; res[LADE_R_KV_SRC] = -1;
-                  res[LADE_R_N_OUT] = st[S_N_OUT]; res[LADE_R_STEPS] = st[S_STEPS]; res[LADE_R_KV_LEN] = st[S_KV_LEN]; }
-    return;
-  }
-  const int phase = meta[LADE_M_PHASE];
+  const int GS = d.GS, WCAP = d.WCAP;
   const int tiny = meta[LADE_M_TINY];
+  const int lg = meta[LADE_M_N_GUESS_TOK];
+  const int phase = meta[LADE_M_PHASE];
+  const int first_guess = am[0];
+  const int* inp = am + 1;
+  const int* gres = am + 1 + WCAP;
+  if (t == 0) { *s_best = 0; dec->first_guess = first_guess; dec->n_new = tiny; }
+  if (t < GS) dec->hits[t] = (t == 0) ? first_guess : 0;
+  for (int j = t; j < tiny; j += blockDim.x) dec->new_tok[j] = inp[j];
+  __syncthreads();
+  if (phase == 2) {
+    const int n_ng = lg / GS;
+    const int* gtok = st + d.off_guess;
+    for (int e0 = 0; e0 < n_ng; e0 += blockDim.x) {
+      const int e = e0 + t;
+      if (e < n_ng) {
+        int gg = GS - 1;
+        for (int u = 0; u < GS; ++u) {
+          const int correct = (u == 0) ? first_guess : gres[e * GS + u - 1];
+          if (gtok[e * GS + u] != correct) { gg = u; break; }
+        }
+        if (gg > 0) atomicMax(s_best, gg * 65536 + (65535 - e));   // strictly longer wins, then earliest
+      }
+    }
+    __syncthreads();
+    const int best = *s_best;
+    if (best > 0) {
+      const int mh = best >> 16, e = 65535 - (best & 0xffff);
+      if (t <= mh) dec->hits[t] = (t == 0) ? first_guess : gres[e * GS + t - 1];
+    }
+  }
+  __syncthreads();
+  if (t == 0) {
+    const int best = *s_best;
+    dec->max_hit = best >> 16;
+    dec->max_hit_idx = best > 0 ? 65535 - (best & 0xffff) : 0;
+  }
+  __syncthreads();
+}
+
+// Reduce the D gathered records to the decision every rank applies (decoding.py:1023-1024,1043-1058,1088-1107).
+__device__ void gathered_decision(const Dims& d, const int* __restrict__ recs, const int* __restrict__ meta, Decision* dec) {
+  const int t = threadIdx.x;
+  const int R = lp_rec_ints(d), GS = d.GS;
+  const int phase = meta[LADE_M_PHASE];
+  __shared__ int s_winner, s_base[65];
+  if (t == 0) {
+    dec->first_guess = recs[0];                          // rank 0's token (torch.distributed.broadcast src=0)
+    int mh = 0, win = 0;
+    for (int r = 0; r < d.D; ++r)
+      if (recs[r * R + 1] > mh) { mh = recs[r * R + 1]; win = r; }      // list.index(max): first rank wins
+    dec->max_hit = mh;
+    dec->max_hit_idx = 0;
+    s_winner = win;
+    int acc = 0;
+    for (int r = 0; r < d.D; ++r) { s_base[r] = acc; acc += recs[r * R + 2]; }
+    s_base[d.D] = acc;
+    dec->n_new = (phase == 0) ? recs[(d.D - 1) * R + 2] : acc;           // prefill: last rank holds all of L1
+  }
+  __syncthreads();
+  if (t < GS) dec->hits[t] = dec->max_hit > 0 ? recs[s_winner * R + 3 + t] : (t == 0 ? dec->first_guess : 0);
+  if (phase == 0) {
+    const int* src = recs + (d.D - 1) * R + 3 + GS;
+    for (int j = t; j < dec->n_new; j += blockDim.x) dec->new_tok[j] = src[j];
+  } else {
+    for (int r = 0; r < d.D; ++r) {
+      const int n = recs[r * R + 2];
+      const int* src = recs + r * R + 3 + GS;
+      for (int j = t; j < n; j += blockDim.x) dec->new_tok[s_base[r] + j] = src[j];
+    }
+  }
+  __syncthreads();
+}
+
+// Apply a decision: window fill/shift, pool update, emission, EOS, KV bookkeeping, result record.
+__device__ void apply_decision(int* st, const Dims& d, const Decision* dec, const int* __restrict__ meta, int* res,
+                               int* s_tup) {
+  const int t = threadIdx.x;
+  const int N = d.N, GS = d.GS, W = d.W;
+  const int phase = meta[LADE_M_PHASE];
   const int n_input = meta[LADE_M_N_INPUT];
   const int q_len = meta[LADE_M_Q_LEN];
   const int lg = meta[LADE_M_N_GUESS_TOK];
   const int kv_len = st[S_KV_LEN];
-  const int first_guess = am[0];
-  const int* inp = am + 1;
-  const int* gres = am + 1 + WCAP;
   int* wl = st + d.off_win_len;
   const int fill = st[S_FILL_LEVEL];
   const int lst_token = st[S_LST_TOKEN];
-  if (t == 0) s_best = 0;
-  if (t < GS) s_hits[t] = (t == 0) ? first_guess : 0;
-  __syncthreads();
+  const int first_guess = dec->first_guess;
+  const int n_new = dec->n_new;
 
   if (phase == 0) {                                                                     // decoding.py:1038-1048
     int* L0 = st_win(st, d, 0);
@@ -262,9 +359,9 @@ __global__ void accept_update_kernel(int* st, Dims d, const int* __restrict__ am
       __syncthreads();
     }
     int* L1 = st_win(st, d, 1);
-    for (int j = t; j < tiny; j += blockDim.x) L1[j] = inp[j];
+    for (int j = t; j < n_new; j += blockDim.x) L1[j] = dec->new_tok[j];
     __syncthreads();
-    if (t == 0) { wl[0] = len0 - 1; wl[1] = tiny; st[S_FILL_LEVEL] = 1; }
+    if (t == 0) { wl[0] = len0 - 1; wl[1] = n_new; st[S_FILL_LEVEL] = 1; }
   } else if (phase == 1) {                                                              // decoding.py:1049-1066
     for (int l = 0; l <= fill; ++l) {
       int* L = st_win(st, d, l);
@@ -279,42 +376,20 @@ __global__ void accept_update_kernel(int* st, Dims d, const int* __restrict__ am
       }
     }
     int* Ln = st_win(st, d, fill + 1);
-    for (int j = t; j + 1 < tiny; j += blockDim.x) Ln[j] = inp[j + 1];
+    for (int j = t; j + 1 < n_new; j += blockDim.x) Ln[j] = dec->new_tok[j + 1];
     __syncthreads();
     if (t == 0) {
       for (int l = 0; l <= fill; ++l) wl[l] = wl[l] - 1;
-      wl[fill + 1] = tiny - 1;
+      wl[fill + 1] = n_new - 1;
       st[S_FILL_LEVEL] = fill + 1;
     }
   } else {
-    // ---- verification: longest matching prefix, earliest n-gram wins (decoding.py:1071-1084)
-    const int n_ng = lg / GS;
-    const int* gtok = st + d.off_guess;
-    for (int e0 = 0; e0 < n_ng; e0 += blockDim.x) {
-      const int e = e0 + t;
-      if (e < n_ng) {
-        int gg = GS - 1;
-        for (int u = 0; u < GS; ++u) {
-          const int correct = (u == 0) ? first_guess : gres[e * GS + u - 1];
-          if (gtok[e * GS + u] != correct) { gg = u; break; }
-        }
-        if (gg > 0) atomicMax(&s_best, gg * 65536 + (65535 - e));
-      }
-    }
-    __syncthreads();
-    const int best = s_best;
-    if (best > 0) {
-      const int mh = best >> 16, e = 65535 - (best & 0xffff);
-      if (t <= mh) s_hits[t] = (t == 0) ? first_guess : gres[e * GS + t - 1];
-    }
     // ---- pool update with the pre-shift window (decoding.py:1116, :37-63)
-    for (int j = t; j < W; j += blockDim.x) s_new[j] = inp[j];
-    __syncthreads();
     if (t < 32) {
       const int* L0 = st_win(st, d, 0);
       for (int i = 0; i < W; ++i) {
         const int key = (i == 0) ? lst_token : L0[i - 1];
-        if (t < GS) s_tup[t] = (t < GS - 1) ? st_win(st, d, t + 1)[i] : s_new[i];
+        if (t < GS) s_tup[t] = (t < GS - 1) ? st_win(st, d, t + 1)[i] : dec->new_tok[i];
         __syncwarp();
         pool_insert_warp(st, d, key, s_tup);
       }
@@ -330,30 +405,31 @@ __global__ void accept_update_kernel(int* st, Dims d, const int* __restrict__ am
       __syncthreads();
     }
     int* Llast = st_win(st, d, N - 2);
-    for (int j = t; j < W; j += blockDim.x) Llast[j] = s_new[j];
+    for (int j = t; j < W; j += blockDim.x) Llast[j] = dec->new_tok[j];
     __syncthreads();
   }
   __syncthreads();
 
-  // ---- emission, EOS scan, POOL_FROM_PROMPT appends, stopping (warp 0; decoding.py:1165-1219)
+  // ---- emission, EOS scan, POOL_FROM_PROMPT appends, stopping (warp 0; decoding.py:1145-1219)
   if (t < 32) {
-    const int best = s_best;
-    const int max_hit = best >> 16;
-    const int max_hit_idx = best > 0 ? 65535 - (best & 0xffff) : 0;
+    const int max_hit = dec->max_hit;
+    const int max_hit_idx = dec->max_hit_idx;
     const int kvcache_len = kv_len + n_input;                                           // modeling :1570
+    // LP with a hit: no KV copy, the accepted tokens are re-fed next step (decoding.py:1148-1153)
+    const bool refeed = (d.D > 1 && max_hit > 0);
     int n_old = st[S_N_OLD];
     int* old = st + d.off_old;
     int n_emit = max_hit + 1;
     bool finished = false;
     for (int h = 0; h <= max_hit; ++h) {
-      if (d.n_eos > 0 && s_hits[h] == d.eos[0]) {
-        if (t == 0 && n_old < d.cap) old[n_old] = s_hits[h];
+      if (d.n_eos > 0 && dec->hits[h] == d.eos[0]) {
+        if (t == 0 && n_old < d.cap) old[n_old] = dec->hits[h];
         n_old++;
         n_emit = h + 1;
         finished = true;
         break;
       }
-      if (t == 0 && n_old < d.cap) old[n_old] = s_hits[max_hit];   // (sic) decoding.py:1175
+      if (t == 0 && n_old < d.cap) old[n_old] = dec->hits[max_hit];   // (sic) decoding.py:1175
       n_old++;
       __syncwarp();
       if (d.pool_from_prompt && n_old >= N && n_old <= d.cap) {                         // decoding.py:1176-1177
@@ -367,30 +443,73 @@ __global__ void accept_update_kernel(int* st, Dims d, const int* __restrict__ am
     }
     const int n_out = st[S_N_OUT];
     int* out = st + d.off_out;
-    if (t < n_emit && n_out + t < d.cap) out[n_out + t] = s_hits[t];
+    if (t < n_emit && n_out + t < d.cap) out[n_out + t] = dec->hits[t];
     __syncwarp();
     if (t == 0) {
       const int n_out_new = n_out + n_emit;
       const int done = (finished || n_out_new >= st[S_MAX_LENGTH]) ? 1 : 0;              // :1215-1219
+      const int kv_new = refeed ? kvcache_len : kvcache_len + max_hit;
       st[S_N_OUT] = n_out_new;
       st[S_N_OLD] = n_old;
-      st[S_KV_LEN] = kvcache_len + max_hit;
-      st[S_LST_TOKEN] = s_hits[max_hit];                                                // :1165
+      st[S_KV_LEN] = kv_new;
+      st[S_SKIP] = refeed ? max_hit : 0;
+      st[S_LST_TOKEN] = dec->hits[max_hit];                                             // :1165
       st[S_DONE] = done;
       st[S_STEPS] = st[S_STEPS] + 1;
       res[LADE_R_N_EMIT] = n_emit;
       res[LADE_R_MAX_HIT] = max_hit;
       res[LADE_R_MAX_HIT_IDX] = max_hit_idx;
-      res[LADE_R_KV_SRC] = max_hit > 0 ? (kv_len + q_len - lg + max_hit_idx * GS) : -1;  // :1156
+      res[LADE_R_KV_SRC] = (max_hit > 0 && !refeed) ? (kv_len + q_len - lg + max_hit_idx * GS) : -1;  // :1156
       res[LADE_R_KV_DST] = kvcache_len;
-      res[LADE_R_KV_LEN] = kvcache_len + max_hit;
+      res[LADE_R_KV_LEN] = kv_new;
       res[LADE_R_DONE] = done;
       res[LADE_R_N_OUT] = n_out_new;
       res[LADE_R_STEPS] = st[S_STEPS];
       res[LADE_R_N_GUESS] = lg / GS;
     }
-    if (t < GS) res[LADE_R_HITS + t] = s_hits[t];
+    if (t < GS) res[LADE_R_HITS + t] = dec->hits[t];
   }
+}
+
+__device__ void write_done_result(int* st, int* res) {
+  if (threadIdx.x == 0) {
+    res[LADE_R_N_EMIT] = 0; res[LADE_R_DONE] = 1; res[LADE_R_MAX_HIT] = 0; res[LADE_R_KV_SRC] = -1;
+    res[LADE_R_N_OUT] = st[S_N_OUT]; res[LADE_R_STEPS] = st[S_STEPS]; res[LADE_R_KV_LEN] = st[S_KV_LEN];
+  }
+}
+
+__global__ void accept_update_kernel(int* st, Dims d, const int* __restrict__ am, const int* __restrict__ meta,
+                                     int* res) {
+  __shared__ Decision dec;
+  __shared__ int s_tup[64];
+  __shared__ int s_best;
+  if (st[S_DONE]) { write_done_result(st, res); return; }
+  local_decision(st, d, am, meta, &dec, &s_best);
+  apply_decision(st, d, &dec, meta, res, s_tup);
+}
+
+// LP, local half: write this rank's record.
+__global__ void lp_verify_kernel(int* st, Dims d, const int* __restrict__ am, const int* __restrict__ meta, int* rec) {
+  __shared__ Decision dec;
+  __shared__ int s_best;
+  const int t = threadIdx.x;
+  if (st[S_DONE]) {
+    for (int i = t; i < lp_rec_ints(d); i += blockDim.x) rec[i] = 0;
+    return;
+  }
+  local_decision(st, d, am, meta, &dec, &s_best);
+  if (t == 0) { rec[0] = dec.first_guess; rec[1] = dec.max_hit; rec[2] = dec.n_new; }
+  if (t < d.GS) rec[3 + t] = dec.hits[t];
+  for (int j = t; j < d.WCAP; j += blockDim.x) rec[3 + d.GS + j] = j < dec.n_new ? dec.new_tok[j] : 0;
+}
+
+// LP, global half: reduce the gathered records and update the (replicated) state.
+__global__ void lp_commit_kernel(int* st, Dims d, const int* __restrict__ recs, const int* __restrict__ meta, int* res) {
+  __shared__ Decision dec;
+  __shared__ int s_tup[64];
+  if (st[S_DONE]) { write_done_result(st, res); return; }
+  gathered_decision(d, recs, meta, &dec);
+  apply_decision(st, d, &dec, meta, res, s_tup);
 }
 
 // ---- KV compaction ---------------------------------------------------------------------------------
@@ -477,6 +596,9 @@ static int make_dims(const LadeConfig& c, Dims* d) {
   d->WCAP = c.window_size + c.level - 3;
   d->V = c.vocab_size; d->cap = c.max_total_len; d->pool_from_prompt = c.pool_from_prompt; d->n_eos = c.n_eos;
   for (int i = 0; i < 4; ++i) d->eos[i] = c.eos_token_id[i];
+  d->D = c.dist_workers > 1 ? c.dist_workers : 1;
+  d->rank = c.dist_workers > 1 ? c.rank : 0;
+  if (d->D > 64 || d->rank < 0 || d->rank >= d->D) return LADE_EINVAL;
   if (d->GS > 63 || d->W > 1024 || d->WCAP > 16384 || d->G > 4096) return LADE_EUNSUPPORTED;
   d->lm_cap = 1 + d->WCAP + d->G * d->GS;
   long long off = S_HDR_INTS;
@@ -556,13 +678,23 @@ int lade_step_layout(LadeCtx* ctx, void* stream, int32_t q_pad, int32_t* ids_out
 
 int lade_step_rows_bound(const LadeConfig* cfg, int32_t n_prompt, int32_t step_index) {
   if (!cfg || cfg->level < 3 || step_index < 0) return LADE_EINVAL;
-  const int W = cfg->window_size, N = cfg->level, G = cfg->guess_set_size;
-  if (step_index == 0) return n_prompt + W + N - 3;
-  if (step_index <= N - 3) {
-    const int k = step_index;
-    return 1 + (W + N - 3 - k) + k * (W + N - 2 - k);
-  }
-  return (N - 1) * (W + (G > 0 ? G : 0));
+  const int W = cfg->window_size, N = cfg->level, G = cfg->guess_set_size > 0 ? cfg->guess_set_size : 0;
+  const int D = cfg->dist_workers > 1 ? cfg->dist_workers : 1;
+  const int rank = D > 1 ? cfg->rank : 0;
+  // level sizes before step k: |L0| = W+N-3-k (k <= N-2), afterwards W-1 ; window_len = |L0|+1
+  const int k = step_index < N - 2 ? step_index : N - 2;
+  const int len0 = W + N - 3 - k;
+  const int window_len = len0 + 1;
+  const int split = (window_len + D - 1) / D;
+  const int ws = D > 1 ? (split * rank < window_len ? split * rank : window_len) : 0;
+  const int we = D > 1 ? (split * (rank + 1) < window_len ? split * (rank + 1) : window_len) : window_len;
+  const int l0_in = we - 1 > 0 ? we - 1 : 0;
+  const int slice = D > 1 ? we - ws : window_len;   // single GPU: |L_l| = |L0|+1 for l >= 1
+  if (step_index == 0) return n_prompt + l0_in;
+  if (step_index <= N - 3) return 1 + l0_in + step_index * slice;
+  const int skip_max = D > 1 ? N - 2 : 0;            // re-fed accepted tokens (decoding.py:1150)
+  const int g_max = (G + D - 1) / D;
+  return 1 + skip_max + l0_in + (N - 2) * slice + g_max * (N - 1);
 }
 
 int lade_accept_update(LadeCtx* ctx, void* stream, const int32_t* argmax_slots, const int32_t* meta,
@@ -627,8 +759,21 @@ int lade_ctx_window_snapshot(LadeCtx* ctx, void* stream, int32_t* win_host, int3
 
 int lade_lp_record_ints(const LadeConfig* cfg) {
   if (!cfg || cfg->level < 3) return LADE_EINVAL;
-  const int D = cfg->dist_workers > 1 ? cfg->dist_workers : 1;
-  return 2 + (cfg->level - 1) + (cfg->window_size + D - 1) / D;
+  return 3 + (cfg->level - 1) + (cfg->window_size + cfg->level - 3);
+}
+
+int lade_lp_verify(LadeCtx* ctx, void* stream, const int32_t* argmax_slots, const int32_t* meta, int32_t* record_out) {
+  if (!ctx || !argmax_slots || !meta || !record_out) return LADE_EINVAL;
+  lp_verify_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(ctx->state, ctx->d, argmax_slots, meta, record_out);
+  LADE_LAUNCH_CHECK("lp_verify_kernel");
+  return LADE_OK;
+}
+
+int lade_lp_commit(LadeCtx* ctx, void* stream, const int32_t* records_all, const int32_t* meta, int32_t* result) {
+  if (!ctx || !records_all || !meta || !result) return LADE_EINVAL;
+  lp_commit_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(ctx->state, ctx->d, records_all, meta, result);
+  LADE_LAUNCH_CHECK("lp_commit_kernel");
+  return LADE_OK;
 }
 
 const char* lade_strerror(int code) {

@@ -92,7 +92,8 @@ class LookaheadEngine:
         self.kv_capacity = self.max_total_len + self.q_steady + self.WCAP + 8
         sm = torch.cuda.get_device_properties(self.dev).multi_processor_count
         q_tiles = (self.q_steady + 127) // 128
-        self.attn_splits = int(attn_splits) if attn_splits else max(1, -(-sm // (self.nh * q_tiles)))
+        # one CTA per SM (TMEM/smem bound): keep the split grid within a single wave
+        self.attn_splits = int(attn_splits) if attn_splits else max(1, sm // (self.nh * q_tiles))
 
         self._fuse_weights()
         self._rope_tables()

@@ -254,12 +254,56 @@ StepFn = Callable[[StepLayout, int], Tuple[int, List[int], List[int]]]
 CompactFn = Callable[[int, int, int, int], None]
 
 
+class LocalComm:
+    """Single-worker stand-in for the LP collectives (lade/decoding.py:906,1024,1045,1057,1090,1096,1106)."""
+    world = 1
+    rank = 0
+
+    def broadcast(self, obj, src):
+        return obj
+
+    def all_gather(self, obj):
+        return [obj]
+
+
+class TorchDistComm:
+    """The same collectives over torch.distributed (gloo on CPU, nccl on GPUs) with object pickling."""
+
+    def __init__(self):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = dist.get_world_size()
+        self.rank = dist.get_rank()
+
+    def broadcast(self, obj, src):
+        box = [obj]
+        self.dist.broadcast_object_list(box, src=src)
+        return box[0]
+
+    def all_gather(self, obj):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+
+def lp_window_slice(window_len: int, D: int, rank: int):
+    """Window columns [ws, we) owned by `rank` (lade/decoding.py:974-977)."""
+    split = (window_len + D - 1) // D
+    return min(split * rank, window_len), min(split * (rank + 1), window_len)
+
+
 def greedy_lookahead(prompt: Sequence[int], max_new: int, W: int, N: int, G: int, step_fn: StepFn,
                      compact_fn: CompactFn, pool_from_prompt: bool = False,
                      eos_token_id=None, rng: Optional[random.Random] = None,
-                     trace: Optional[List[StepTrace]] = None, token_map_out: Optional[dict] = None):
-    """Restatement of jacobi_greedy_search_multilevel (single worker). Returns (ids, steps)."""
+                     trace: Optional[List[StepTrace]] = None, token_map_out: Optional[dict] = None,
+                     comm=None):
+    """Restatement of jacobi_greedy_search_multilevel, incl. lookahead parallelism. Returns (ids, steps).
+
+    `comm` = None/LocalComm for one worker, TorchDistComm under LP (DIST_WORKERS = comm.world).
+    """
     assert N >= 3, "LEVEL must be >= 3 (past_tokens[1] must exist, decoding.py:902)"
+    comm = comm or LocalComm()
+    D, RANK = comm.world, comm.rank
     rng = rng or random
     if isinstance(eos_token_id, int):
         eos_token_id = [eos_token_id]                                                    # :820-821
@@ -268,27 +312,37 @@ def greedy_lookahead(prompt: Sequence[int], max_new: int, W: int, N: int, G: int
     out_ids = list(prompt)
     max_length = init_len + max_new
     past_tokens: List[Optional[List[int]]] = [[rng.choice(all_old) for _ in range(W + N - 3)]] + [None] * (N - 2)  # :902
+    if D > 1:
+        past_tokens = comm.broadcast(past_tokens, 0)                                     # :906
     fill_level = 0
     token_map: Dict[int, list] = token_map_out if token_map_out is not None else {}
     steps = 0
     lst_token = None
+    guess_skip_dist = 0
     if pool_from_prompt:
         fill_pool_with_prompt(all_old, token_map, N, G)                                  # :915-916
     kv_len = 0
     first = True
+    GS = N - 1
     while True:
-        if first:
-            tail = out_ids
-        else:
-            tail = out_ids[-1:]
+        tail = out_ids if first else out_ids[-1 - guess_skip_dist:]                      # :938-942
         lst_id = len(out_ids) - 1
         if past_tokens[N - 2] is not None and lst_token in token_map and G > 0:          # :948
             guess_tokens = [t for tup in token_map[lst_token] for t in tup]
+            if D > 1:                                                                    # :956-963
+                cnt = (len(guess_tokens) // GS + D - 1) // D
+                guess_tokens = guess_tokens[GS * cnt * RANK: GS * cnt * (RANK + 1)]
             if len(guess_tokens) == 0:
                 guess_tokens = None
         else:
             guess_tokens = None
-        lay = build_step_layout(tail, lst_id, past_tokens, fill_level, guess_tokens, N, first)
+        if D > 1:                                                                        # :973-984
+            window_len = len(past_tokens[0]) + 1
+            ws, we = lp_window_slice(window_len, D, RANK)
+            past_inp = [past_tokens[0][: we - 1]] + [t[ws:we] if t is not None else None for t in past_tokens[1:]]
+        else:
+            past_inp = past_tokens
+        lay = build_step_layout(tail, lst_id, past_inp, fill_level, guess_tokens, N, first)
         out_tok, inp_toks, guess_res = step_fn(lay, kv_len)
         steps += 1
         tr = StepTrace(ids=list(lay.ids), pos=list(lay.pos), level_sizes=list(lay.level_sizes),
@@ -298,35 +352,56 @@ def greedy_lookahead(prompt: Sequence[int], max_new: int, W: int, N: int, G: int
         kvcache_len = kv_len + lay.n_input                                               # modeling :1570
         step_len = kv_len + lay.q_len                                                    # modeling :1571
         first_guess = out_tok
+        if D > 1:
+            first_guess = comm.broadcast(first_guess, 0)                                 # :1024
         max_hit, max_hit_idx = 0, 0
         hits = [first_guess] + [0] * (N - 2)
         if past_tokens[1] is None:                                                       # :1038
             past_tokens[0] = past_tokens[0][1:]
             past_tokens[1] = list(inp_toks)
+            if D > 1:
+                past_tokens[1] = comm.broadcast(past_tokens[1], D - 1)                   # :1045
             fill_level += 1
         elif past_tokens[N - 2] is None:                                                 # :1049
             for level in range(fill_level + 1):
                 past_tokens[level] = past_tokens[level][1:]
-            past_tokens[fill_level + 1] = list(inp_toks)[1:]
+            current = list(inp_toks)
+            if D > 1:
+                current = sum(comm.all_gather(current), [])                              # :1057-1058
+            past_tokens[fill_level + 1] = current[1:]
             fill_level += 1
         else:
             if guess_tokens is not None:
                 max_hit, max_hit_idx, hits = verify_guesses(first_guess, guess_tokens, guess_res, N)
+            if D > 1:                                                                    # :1088-1097
+                all_hits = comm.all_gather(max_hit)
+                max_hit = max(all_hits)
+                winner = all_hits.index(max_hit)
+                if max_hit > 0:
+                    hits = comm.broadcast(hits, winner)
             new_results = list(inp_toks)
+            if D > 1:
+                new_results = sum(comm.all_gather(new_results), [])                      # :1106-1107
             assert len(past_tokens[N - 2]) == W and len(new_results) == W                # :1114
             update_token_map(token_map, lst_token, past_tokens, new_results, N, W, G)    # :1116
             past_tokens[0] = past_tokens[1][1:]                                          # :1120
             for level in range(1, N - 2):
                 past_tokens[level] = past_tokens[level + 1][:]
             past_tokens[N - 2] = new_results
-        # KV compaction (:1156-1163)
-        if max_hit > 0:
-            src = step_len - len(guess_tokens) + max_hit_idx * (N - 1)
-            tr.kv_src = src
-            compact_fn(kvcache_len, src, max_hit, kvcache_len + max_hit)
-        else:
+        # KV handling (:1145-1163)
+        if D > 1 and max_hit > 0:
+            guess_skip_dist = max_hit              # accepted tokens are re-fed next step, no KV copy
             compact_fn(kvcache_len, 0, 0, kvcache_len)
-        kv_len = kvcache_len + max_hit
+            kv_len = kvcache_len
+        else:
+            guess_skip_dist = 0
+            if max_hit > 0:
+                src = step_len - len(guess_tokens) + max_hit_idx * GS
+                tr.kv_src = src
+                compact_fn(kvcache_len, src, max_hit, kvcache_len + max_hit)
+            else:
+                compact_fn(kvcache_len, 0, 0, kvcache_len)
+            kv_len = kvcache_len + max_hit
         lst_token = hits[max_hit]                                                        # :1165
         n_emit = max_hit + 1
         for hit_idx in range(max_hit + 1):                                               # :1168-1177

@@ -50,6 +50,8 @@ GREEDY_CASES = [
 
 
 def _margins(logits_rows: torch.Tensor):
+    if logits_rows.numel() == 0:          # LP rank with an empty window slice
+        return torch.tensor([float("inf")])
     top2 = torch.topk(logits_rows.float(), 2, dim=-1).values
     return (top2[..., 0] - top2[..., 1])
 
@@ -136,7 +138,8 @@ def trace_reference_greedy(model, prompt, max_new, lade_cfg, py_seed=0, eos=None
         modeling.j_make_causal_mask_multilevel = orig_mask
     tm = token_map_ref.get("tm", {})
     pool = {str(k): [list(t) for t in v] for k, v in tm.items()}
-    log = decoding.CONFIG_MAP["log"][-1]
+    logs = decoding.CONFIG_MAP.get("log") or []
+    log = logs[-1] if logs else [out.shape[1] - prompt.shape[1], len(steps), 0.0]   # only LOCAL_RANK 0 logs (:1231)
     return out[0].tolist(), steps, pool, log, attn_io
 
 
