@@ -177,6 +177,15 @@ int lade_argmax_rows(void* stream, const void* logits, int32_t n_rows, int32_t v
 int lade_accept_update(LadeCtx* ctx, void* stream, const int32_t* argmax_slots, const int32_t* meta,
                        int32_t* result);
 
+/* Apply an externally made decision (sampling path: the caller runs the reference's rejection-sampling
+ * verification, lade/decoding.py:484-540, against the device logits with its own RNG streams).
+ * `decision` (device) = lade_lp_record_ints() ints [first_token, max_hit, n_new, hits[N-1], new_window_tokens[W+N-3]]
+ * followed by [max_hit_idx, flags, finished, 0] and, when flags bit1 is set, W ints: the newest window level
+ * after filter_window (decoding.py:131-135,578-580; the pool still receives the unfiltered tokens).
+ * flags bit0: sampling emission semantics (decoding.py:594-603). */
+int lade_commit_decision(LadeCtx* ctx, void* stream, const int32_t* decision, const int32_t* meta,
+                         int32_t* result);
+
 /* Move the accepted n-gram's K/V rows to the cache tail for every layer (lade/decoding.py:1156-1163).
  * k_base/v_base point at layer 0; layers are `layer_stride_elems` apart. */
 int lade_kv_compact(void* stream, const int32_t* result, void* k_base, void* v_base,

@@ -257,6 +257,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else {
     // ================= softmax: one thread per query row =================
+    // Code size matters here (the instruction cache is 32 KB): S is consumed in 32-column chunks by rolled
+    // loops, in two passes over TMEM (row max, then exp/P) instead of holding 128 scores in registers.
     const int quad = warp & 3;
     const int row_l = quad * 32 + lane;             // TMEM lane == row inside the tile
     const int row = mt * TC_BM + row_l;             // step-local row
@@ -264,36 +266,46 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int* rdp = rd_in_smem ? s_rd : rowdesc;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     float m_used = -INFINITY, l_sum = 0.f;
-    float sv[128];
     for (int j = 0; j < my_tiles; ++j) {
       const int buf = j & 1, s = j % TC_STAGES;
       mbar_wait(BAR(B_SFULL + buf), (j >> 1) & 1);
       tc_fence_after();
       const uint32_t ts = tmem_base + lane_addr + (uint32_t)buf * 128u;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(ts + c * 32, sv + c * 32);
-      tmem_ld_wait();
       const int col0 = (tile_lo + j) * TC_BN;
-      const bool need_mask = (col0 + TC_BN > kv_len);
-      float mx = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 128; ++i) {
-        float x = bf16_round(bf16_round(sv[i]) * inv_sqrt_d);
-        if (need_mask) {
-          const int col = col0 + i;
-          bool vis;
-          if (col < kv_len) vis = true;
-          else if (col >= T) vis = false;
-          else {
-            const int c = col - kv_len;
-            if (is_prefill) vis = (row < q_len) ? (c <= row) : (c == row);
-            else vis = row_sees(rd_r, row, rdp[c], c, level_offset);
+      // visibility bits of this row for the 128 columns of the tile (all ones for pure-cache tiles)
+      uint32_t mb0 = 0xffffffffu, mb1 = 0xffffffffu, mb2 = 0xffffffffu, mb3 = 0xffffffffu;
+      if (col0 + TC_BN > kv_len) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t bits = 0;
+#pragma unroll 1
+          for (int i = 0; i < 32; ++i) {
+            const int col = col0 + c * 32 + i;
+            bool vis;
+            if (col < kv_len) vis = true;
+            else if (col >= T) vis = false;
+            else {
+              const int cc = col - kv_len;
+              if (is_prefill) vis = (row < q_len) ? (cc <= row) : (cc == row);
+              else vis = row_sees(rd_r, row, rdp[cc], cc, level_offset);
+            }
+            bits |= (vis ? 1u : 0u) << i;
           }
-          if (!vis) x = -INFINITY;
+          if (c == 0) mb0 = bits; else if (c == 1) mb1 = bits; else if (c == 2) mb2 = bits; else mb3 = bits;
         }
-        sv[i] = x;
-        mx = fmaxf(mx, x);
       }
+      // pass 1: row max.  bf16 rounding and the positive scale are monotone, so round the max once.
+      float mx_raw = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+        tmem_ld32(ts + c * 32, v);
+        tmem_ld_wait();
+        const uint32_t mb = c == 0 ? mb0 : (c == 1 ? mb1 : (c == 2 ? mb2 : mb3));
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx_raw = fmaxf(mx_raw, ((mb >> i) & 1u) ? v[i] : -INFINITY);
+      }
+      const float mx = (mx_raw == -INFINITY) ? -INFINITY : bf16_round(bf16_round(mx_raw) * inv_sqrt_d);
       // lazy rescale: keep the stale max while it is within 2^8 of the running max
       if (j == 0) {
         m_used = mx;
@@ -305,9 +317,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const float m_new = fmaxf(m_used, mx);
           const float scale = (m_new == -INFINITY) ? 1.f : exp2f((m_used - m_new) * TC_LOG2E);
           l_sum *= scale;
-          float ov[32];
-#pragma unroll
+#pragma unroll 1
           for (int c = 0; c < 4; ++c) {
+            float ov[32];
             tmem_ld32(tmem_O + lane_addr + c * 32, ov);
             tmem_ld_wait();
 #pragma unroll
@@ -319,22 +331,33 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
       const float off = (m_used == -INFINITY) ? 0.f : m_used * TC_LOG2E;
-      // P (bf16) into the K stage, K-major SWIZZLE_128B: [kv block of 64][row][128 B], 16 B chunk ^ (row & 7)
+      // pass 2: P = exp2(score - max) as bf16 into the K stage, K-major SWIZZLE_128B:
+      //         [kv block of 64][row][128 B], 16-byte chunk index ^ (row & 7)
       unsigned char* pK = smem + TC_TILE_BYTES * (1 + 2 * s);
       float psum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+        tmem_ld32(ts + c * 32, v);
+        tmem_ld_wait();
+        const uint32_t mb = c == 0 ? mb0 : (c == 1 ? mb1 : (c == 2 ? mb2 : mb3));
+        unsigned char* prow = pK + (c >> 1) * TC_HALF_BYTES + row_l * 128;
 #pragma unroll
-      for (int ch = 0; ch < 16; ++ch) {
-        float p[8];
+        for (int g = 0; g < 4; ++g) {
+          float p[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          p[e] = exp2f(sv[ch * 8 + e] * TC_LOG2E - off);
-          psum += p[e];
+          for (int e = 0; e < 8; ++e) {
+            const int i = g * 8 + e;
+            const float x = bf16_round(bf16_round(v[i]) * inv_sqrt_d);        // reference rounding points
+            p[e] = ((mb >> i) & 1u) ? exp2f(x * TC_LOG2E - off) : 0.f;
+            psum += p[e];
+          }
+          uint4 pk;
+          pk.x = pack2_bf16(p[0], p[1]); pk.y = pack2_bf16(p[2], p[3]);
+          pk.z = pack2_bf16(p[4], p[5]); pk.w = pack2_bf16(p[6], p[7]);
+          const int cc = (c & 1) * 4 + g;
+          *reinterpret_cast<uint4*>(prow + ((cc ^ (row_l & 7)) << 4)) = pk;
         }
-        uint4 pk;
-        pk.x = pack2_bf16(p[0], p[1]); pk.y = pack2_bf16(p[2], p[3]);
-        pk.z = pack2_bf16(p[4], p[5]); pk.w = pack2_bf16(p[6], p[7]);
-        const int kb = ch >> 3, cc = ch & 7;
-        *reinterpret_cast<uint4*>(pK + kb * TC_HALF_BYTES + row_l * 128 + ((cc ^ (row_l & 7)) << 4)) = pk;
       }
       l_sum += psum;
       // stale cache rows past T must not reach the PV MMA (0 * NaN): zero them in the staged V tile
@@ -343,7 +366,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (col0 + row_l >= T) {
           unsigned char* pV = smem + TC_TILE_BYTES * (2 + 2 * s);
           const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll
+#pragma unroll 1
           for (int cc = 0; cc < 8; ++cc) {
             *reinterpret_cast<uint4*>(pV + row_l * 128 + cc * 16) = z;
             *reinterpret_cast<uint4*>(pV + TC_HALF_BYTES + row_l * 128 + cc * 16) = z;
@@ -362,7 +385,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const long long rows_pad = (long long)q_tiles * TC_BM;
     if (n_active == 1) {
       const float inv = l_sum > 0.f ? 1.f / l_sum : 0.f;
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         float ov[32];
         tmem_ld32(tmem_O + lane_addr + c * 32, ov);
@@ -383,7 +406,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     } else {
       float* po = part_o + (((long long)split * n_heads + h) * rows_pad + row) * TC_D;
       float* pml = part_ml + (((long long)split * n_heads + h) * rows_pad + row) * 2;
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         float ov[32];
         tmem_ld32(tmem_O + lane_addr + c * 32, ov);

@@ -246,8 +246,11 @@ __global__ void step_layout_kernel(int* st, Dims d, int q_pad, int* ids_out, int
 //   record = [first_guess, max_hit, n_new, hits[GS], new_tokens[WCAP]]
 struct Decision {
   int first_guess, max_hit, max_hit_idx, n_new;
+  int sampling;        // sampling-path semantics of the emission loop (decoding.py:594-603)
+  int extra_finished;  // host-evaluated stop condition (sampling path, decoding.py:636-643)
   int hits[64];
   int new_tok[1024 + 64];
+  int filt[1024];      // sampling + EOS: newest window level after filter_window (decoding.py:131-135,578-580)
 };
 
 __device__ __forceinline__ int lp_rec_ints(const Dims& d) { return 3 + d.GS + d.WCAP; }
@@ -263,7 +266,7 @@ __device__ void local_decision(int* st, const Dims& d, const int* __restrict__ a
   const int first_guess = am[0];
   const int* inp = am + 1;
   const int* gres = am + 1 + WCAP;
-  if (t == 0) { *s_best = 0; dec->first_guess = first_guess; dec->n_new = tiny; }
+  if (t == 0) { *s_best = 0; dec->first_guess = first_guess; dec->n_new = tiny; dec->sampling = 0; dec->extra_finished = 0; }
   if (t < GS) dec->hits[t] = (t == 0) ? first_guess : 0;
   for (int j = t; j < tiny; j += blockDim.x) dec->new_tok[j] = inp[j];
   __syncthreads();
@@ -304,6 +307,7 @@ __device__ void gathered_decision(const Dims& d, const int* __restrict__ recs, c
   const int phase = meta[LADE_M_PHASE];
   __shared__ int s_winner, s_base[65];
   if (t == 0) {
+    dec->sampling = 0; dec->extra_finished = 0;
     dec->first_guess = recs[0];                          // rank 0's token (torch.distributed.broadcast src=0)
     int mh = 0, win = 0;
     for (int r = 0; r < d.D; ++r)
@@ -405,7 +409,7 @@ __device__ void apply_decision(int* st, const Dims& d, const Decision* dec, cons
       __syncthreads();
     }
     int* Llast = st_win(st, d, N - 2);
-    for (int j = t; j < W; j += blockDim.x) Llast[j] = dec->new_tok[j];
+    for (int j = t; j < W; j += blockDim.x) Llast[j] = (dec->sampling & 2) ? dec->filt[j] : dec->new_tok[j];
     __syncthreads();
   }
   __syncthreads();
@@ -429,7 +433,8 @@ __device__ void apply_decision(int* st, const Dims& d, const Decision* dec, cons
         finished = true;
         break;
       }
-      if (t == 0 && n_old < d.cap) old[n_old] = dec->hits[max_hit];   // (sic) decoding.py:1175
+      // greedy path appends the LAST hit every time (sic, decoding.py:1175); the sampling path the right one (:601)
+      if (t == 0 && n_old < d.cap) old[n_old] = (dec->sampling & 1) ? dec->hits[h] : dec->hits[max_hit];
       n_old++;
       __syncwarp();
       if (d.pool_from_prompt && n_old >= N && n_old <= d.cap) {                         // decoding.py:1176-1177
@@ -439,7 +444,8 @@ __device__ void apply_decision(int* st, const Dims& d, const Decision* dec, cons
       }
     }
     if (!finished) {
-      for (int k = 0; k < d.n_eos; ++k) finished = finished || (first_guess == d.eos[k]);  // :1205-1212
+      if (dec->sampling & 1) finished = dec->extra_finished != 0;
+      else for (int k = 0; k < d.n_eos; ++k) finished = finished || (first_guess == d.eos[k]);  // :1205-1212
     }
     const int n_out = st[S_N_OUT];
     int* out = st + d.off_out;
@@ -485,6 +491,26 @@ __global__ void accept_update_kernel(int* st, Dims d, const int* __restrict__ am
   __shared__ int s_best;
   if (st[S_DONE]) { write_done_result(st, res); return; }
   local_decision(st, d, am, meta, &dec, &s_best);
+  apply_decision(st, d, &dec, meta, res, s_tup);
+}
+
+// Externally decided step (sampling path: the host runs the reference's rejection-sampling verification,
+// decoding.py:484-540, with the python/torch RNG streams): apply [record | max_hit_idx, flags, finished].
+__global__ void commit_decision_kernel(int* st, Dims d, const int* __restrict__ rec, const int* __restrict__ meta, int* res) {
+  __shared__ Decision dec;
+  __shared__ int s_tup[64];
+  const int t = threadIdx.x;
+  if (st[S_DONE]) { write_done_result(st, res); return; }
+  const int R = lp_rec_ints(d);
+  if (t == 0) {
+    dec.first_guess = rec[0]; dec.max_hit = rec[1]; dec.n_new = rec[2];
+    dec.max_hit_idx = rec[R]; dec.sampling = rec[R + 1] & 3; dec.extra_finished = rec[R + 2];
+  }
+  if (rec[R + 1] & 2)
+    for (int j = t; j < d.W; j += blockDim.x) dec.filt[j] = rec[R + 4 + j];
+  if (t < d.GS) dec.hits[t] = rec[3 + t];
+  for (int j = t; j < d.WCAP; j += blockDim.x) dec.new_tok[j] = rec[3 + d.GS + j];
+  __syncthreads();
   apply_decision(st, d, &dec, meta, res, s_tup);
 }
 
@@ -760,6 +786,14 @@ int lade_ctx_window_snapshot(LadeCtx* ctx, void* stream, int32_t* win_host, int3
 int lade_lp_record_ints(const LadeConfig* cfg) {
   if (!cfg || cfg->level < 3) return LADE_EINVAL;
   return 3 + (cfg->level - 1) + (cfg->window_size + cfg->level - 3);
+}
+
+int lade_commit_decision(LadeCtx* ctx, void* stream, const int32_t* decision, const int32_t* meta, int32_t* result) {
+  if (!ctx || !decision || !meta || !result) return LADE_EINVAL;
+  if (ctx->d.D != 1) return LADE_ESTATE;   // the sampling path has no LP (reference: replicas only)
+  commit_decision_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(ctx->state, ctx->d, decision, meta, result);
+  LADE_LAUNCH_CHECK("commit_decision_kernel");
+  return LADE_OK;
 }
 
 int lade_lp_verify(LadeCtx* ctx, void* stream, const int32_t* argmax_slots, const int32_t* meta, int32_t* record_out) {

@@ -90,6 +90,9 @@ def get_engine(model, **overrides) -> LookaheadEngine:
     pool = bool(CONFIG_MAP.get("POOL_FROM_PROMPT", 0))
     overrides = {**CONFIG_MAP.get("ENGINE_OVERRIDES", {}), **overrides}
     cap = int(overrides.pop("max_total_len", CONFIG_MAP.get("MAX_TOTAL_LEN", 4096)))
+    if CONFIG_MAP.get("DIST_WORKERS", 1) > 1:                         # lookahead parallelism (lade/utils.py:28-33)
+        overrides.setdefault("dist_workers", CONFIG_MAP["DIST_WORKERS"])
+        overrides.setdefault("rank", CONFIG_MAP.get("LOCAL_RANK", 0))
     key = (W, N, G, pool, tuple(sorted(overrides.items())))
     cache = model.__dict__.setdefault("_lade_engines", {})
     eng = cache.get(key)

@@ -51,7 +51,8 @@ class LookaheadEngine:
 
     def __init__(self, model, window_size: int, level: int, guess_set_size: int,
                  pool_from_prompt: bool = False, max_total_len: int = 4096, attn_impl: int = 0,
-                 attn_splits: Optional[int] = None, use_cuda_graph: bool = True, debug: bool = False):
+                 attn_splits: Optional[int] = None, use_cuda_graph: bool = True, debug: bool = False,
+                 dist_workers: int = 1, rank: int = 0, process_group=None):
         self.lib = _cabi.load()
         cfg = model.config
         p0 = next(model.parameters())
@@ -87,8 +88,20 @@ class LookaheadEngine:
         self.use_cuda_graph = use_cuda_graph
         self.debug = debug
         self.lm_cap = 1 + self.WCAP + self.G * self.GS
-        self.q_steady = self.GS * (self.W + max(self.G, 0))
+        # lookahead parallelism (lade_distributed): full replica per rank, window/guess slices per rank
+        self.DW = int(dist_workers) if dist_workers and dist_workers > 1 else 1
+        self.rank = int(rank) if self.DW > 1 else 0
+        self.pg = process_group
+        if self.DW > 1:
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                raise LadeError("DIST_WORKERS > 1 needs an initialised torch.distributed process group")
+            if dist.get_world_size(self.pg) != self.DW:
+                raise LadeError("DIST_WORKERS config should be equal to work size")      # lade/utils.py:33
         self.max_total_len = int(max_total_len)
+        probe = self._make_config(())
+        self.q_steady = int(self.lib.lade_step_rows_bound(C.byref(probe), 1, self.N))    # fixed steady shape
+        self.rec_ints = int(self.lib.lade_lp_record_ints(C.byref(probe)))
         self.kv_capacity = self.max_total_len + self.q_steady + self.WCAP + 8
         sm = torch.cuda.get_device_properties(self.dev).multi_processor_count
         q_tiles = (self.q_steady + 127) // 128
@@ -159,6 +172,8 @@ class LookaheadEngine:
         self.lm_rows = torch.zeros(self.lm_cap, **i32)
         self.am = torch.zeros(self.lm_cap, **i32)
         self.res = torch.zeros(_cabi.RES_INTS, **i32)
+        self.lp_send = torch.zeros(self.rec_ints, **i32)
+        self.lp_recv = torch.zeros(self.DW * self.rec_ints, **i32)
         self.h = torch.empty(rows, self.H, dtype=bf, device=dev)
         self.xn = torch.empty(rows, self.H, dtype=bf, device=dev)
         self.qkv = torch.empty(rows, (self.nh + 2 * self.nkv) * self.D, dtype=bf, device=dev)
@@ -176,6 +191,18 @@ class LookaheadEngine:
         self.attn_scratch = torch.zeros(int(nbytes), dtype=torch.uint8, device=dev)
 
     # ------------------------------------------------------------------------------------------
+    def _make_config(self, eos_ids) -> LadeConfig:
+        c = LadeConfig()
+        c.window_size, c.level, c.guess_set_size = self.W, self.N, self.G
+        c.pool_from_prompt = int(self.pool_from_prompt)
+        c.vocab_size = self.V
+        c.max_total_len = self.max_total_len + self.N + 8
+        c.n_eos = len(eos_ids)
+        for i, e in enumerate(eos_ids):
+            c.eos_token_id[i] = int(e)
+        c.dist_workers, c.rank = self.DW, self.rank
+        return c
+
     def _ensure_ctx(self, eos_ids: Sequence[int]):
         eos_ids = list(eos_ids)[:4]
         key = (tuple(eos_ids),)
@@ -185,15 +212,7 @@ class LookaheadEngine:
             self.lib.lade_ctx_destroy(self._ctx)
             self._ctx = C.c_void_p()
             self._graph = None
-        c = LadeConfig()
-        c.window_size, c.level, c.guess_set_size = self.W, self.N, self.G
-        c.pool_from_prompt = int(self.pool_from_prompt)
-        c.vocab_size = self.V
-        c.max_total_len = self.max_total_len + self.N + 8
-        c.n_eos = len(eos_ids)
-        for i, e in enumerate(eos_ids):
-            c.eos_token_id[i] = int(e)
-        c.dist_workers, c.rank = 1, 0
+        c = self._make_config(eos_ids)
         check(self.lib.lade_ctx_create(C.byref(c), C.byref(self._ctx)), "lade_ctx_create")
         self._lcfg = c
         self._ctx_key = key
@@ -210,8 +229,9 @@ class LookaheadEngine:
             pass
 
     # ------------------------------------------------------------------------------------------
-    def _launch_step(self, rows: int, stream: int):
-        """All launches of one step on `stream` for `rows` materialised rows (rows <= rows_cap)."""
+    def _launch_step(self, rows: int, stream: int, commit: bool = True):
+        """All launches of one step on `stream` for `rows` materialised rows (rows <= rows_cap).
+        commit=False stops after the row-wise argmax (the sampling path decides on the host)."""
         lib, L = self.lib, self.L
         n = 0
         check(lib.lade_step_layout(self._ctx, stream, rows, _ptr(self.ids), _ptr(self.pos), _ptr(self.rowdesc),
@@ -246,12 +266,30 @@ class LookaheadEngine:
         torch.mm(self.xn_lm, self.lm_head.t(), out=self.logits)
         check(lib.lade_argmax_rows(stream, _ptr(self.logits), self.lm_cap, self.V, self.V, _ptr(self.am)),
               "lade_argmax_rows"); n += 1
-        check(lib.lade_accept_update(self._ctx, stream, _ptr(self.am), _ptr(self.meta), _ptr(self.res)),
-              "lade_accept_update"); n += 1
-        check(lib.lade_kv_compact(stream, _ptr(self.res), _ptr(self.kv[0, 0]), _ptr(self.kv[0, 1]),
-                                  self.kv.stride(0), self.L, self.nkv, self.kv_capacity, self.D, max(self.GS - 1, 1)),
-              "lade_kv_compact"); n += 1
+        if not commit:
+            return n
+        if self.DW == 1:
+            n += self._launch_commit(stream)
+        else:   # LP: local verify here (capturable); exchange + commit follow in _launch_commit
+            check(lib.lade_lp_verify(self._ctx, stream, _ptr(self.am), _ptr(self.meta), _ptr(self.lp_send)),
+                  "lade_lp_verify"); n += 1
         return n
+
+    def _launch_commit(self, stream: int) -> int:
+        """State update of the step.  Single GPU: fused verify+accept+update, then KV compaction.
+        LP: one all-gather of the fixed-size per-rank records over NCCL, then the replicated commit."""
+        lib = self.lib
+        if self.DW == 1:
+            check(lib.lade_accept_update(self._ctx, stream, _ptr(self.am), _ptr(self.meta), _ptr(self.res)),
+                  "lade_accept_update")
+            check(lib.lade_kv_compact(stream, _ptr(self.res), _ptr(self.kv[0, 0]), _ptr(self.kv[0, 1]),
+                                      self.kv.stride(0), self.L, self.nkv, self.kv_capacity, self.D, max(self.GS - 1, 1)),
+                  "lade_kv_compact")
+            return 2
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(self.lp_recv, self.lp_send, group=self.pg)
+        check(lib.lade_lp_commit(self._ctx, stream, _ptr(self.lp_recv), _ptr(self.meta), _ptr(self.res)), "lade_lp_commit")
+        return 1
 
     def _read_result(self) -> StepRecord:
         self._pinned_res.copy_(self.res, non_blocking=True)
@@ -262,38 +300,39 @@ class LookaheadEngine:
                           hits=[int(x) for x in r[_cabi.R_HITS:_cabi.R_HITS + n_emit]],
                           n_guess=int(r[_cabi.R_N_GUESS]), kv_len=int(r[_cabi.R_KV_LEN]), done=bool(r[_cabi.R_DONE]))
 
-    def _steady_graph(self):
-        if self._graph is not None:
-            return self._graph
+    def _steady_graph(self, commit: bool = True):
+        if self._graph is None:
+            self._graph = {}
+        if commit in self._graph:
+            return self._graph[commit][0]
         rows = self.q_steady
         g = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):
             with torch.cuda.graph(g, stream=side):
-                self._launches_per_graph = self._launch_step(rows, torch.cuda.current_stream(self.dev).cuda_stream)
+                n = self._launch_step(rows, torch.cuda.current_stream(self.dev).cuda_stream, commit=commit)
         torch.cuda.current_stream(self.dev).wait_stream(side)
-        self._graph = g
+        self._graph[commit] = (g, n)
+        self._launches_per_graph = n
         return g
 
-    # ------------------------------------------------------------------------------------------
-    @torch.no_grad()
-    def generate(self, prompt_ids: Sequence[int], max_new_tokens: int, eos_token_ids: Sequence[int] = (),
-                 rng: Optional[random.Random] = None, window0: Optional[Sequence[int]] = None) -> List[int]:
-        """Greedy lookahead decoding; returns prompt + generated ids (trimmed to P + max_new_tokens).
+    def run_forward_step(self, step: int, n_prompt: int, commit: bool = True) -> None:
+        """One step's launches (eager for the prefill / window-fill steps, graph replay afterwards)."""
+        stream = torch.cuda.current_stream(self.dev).cuda_stream
+        if step <= self.N - 3 or not self.use_cuda_graph:
+            rows = self.lib.lade_step_rows_bound(C.byref(self._lcfg), n_prompt, step)
+            if rows < 0:
+                raise LadeError("lade_step_rows_bound failed")
+            self.launches += self._launch_step(min(rows, self.rows_cap), stream, commit=commit)
+        else:
+            self._steady_graph(commit).replay()
+            self.launches += self._graph[commit][1]
 
-        The initial window is drawn on the host exactly as lade/decoding.py:887-902 does
-        (``random.choice`` over the prompt, W+N-3 draws) so the python RNG stream matches the reference.
-        """
-        prompt = [int(t) for t in prompt_ids]
+    def begin(self, prompt, max_length: int, eos_token_ids, window0) -> None:
+        """Reset the device state for a generate() call (lade_ctx_reset) and size the buffers."""
         P = len(prompt)
-        max_length = P + int(max_new_tokens)
-        if max_length > self.max_total_len:
-            raise LadeError(f"prompt+max_new_tokens={max_length} exceeds engine capacity {self.max_total_len}")
         self._ensure_ctx(eos_token_ids)
-        rnd = rng or random
-        if window0 is None:
-            window0 = [rnd.choice(prompt) for _ in range(self.WCAP)]
         stream = torch.cuda.current_stream(self.dev).cuda_stream
         prompt_np = np.asarray(prompt, dtype=np.int32)
         win_np = np.asarray(list(window0), dtype=np.int32)
@@ -301,24 +340,44 @@ class LookaheadEngine:
                                       max_length), "lade_ctx_reset")
         torch.cuda.current_stream(self.dev).synchronize()   # host buffers were consumed
         self.launches += 2 + int(self.pool_from_prompt)
-        rows0 = P + self.WCAP
+        rows0 = int(self.lib.lade_step_rows_bound(C.byref(self._lcfg), P, 0))
         if rows0 > self.rows_cap:
             self._graph = None
             self._alloc(rows0)
+
+    def draw_window(self, prompt, rng=None, window0=None):
+        """Initial lookahead window: W+N-3 draws of random.choice(prompt), exactly as lade/decoding.py:887-902
+        (same python RNG consumption); under LP rank 0's draw is broadcast (:905-906)."""
+        rnd = rng or random
+        if window0 is None:
+            window0 = [rnd.choice(prompt) for _ in range(self.WCAP)]
+        if self.DW > 1:
+            import torch.distributed as dist
+            wt = torch.tensor(list(window0), dtype=torch.int32, device=self.dev)
+            dist.broadcast(wt, src=dist.get_global_rank(self.pg, 0) if self.pg is not None else 0, group=self.pg)
+            window0 = wt.cpu().tolist()
+        return list(window0)
+
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def generate(self, prompt_ids: Sequence[int], max_new_tokens: int, eos_token_ids: Sequence[int] = (),
+                 rng: Optional[random.Random] = None, window0: Optional[Sequence[int]] = None) -> List[int]:
+        """Greedy lookahead decoding; returns prompt + generated ids (trimmed to P + max_new_tokens)."""
+        prompt = [int(t) for t in prompt_ids]
+        P = len(prompt)
+        max_length = P + int(max_new_tokens)
+        if max_length > self.max_total_len:
+            raise LadeError(f"prompt+max_new_tokens={max_length} exceeds engine capacity {self.max_total_len}")
+        self.begin(prompt, max_length, eos_token_ids, self.draw_window(prompt, rng, window0))
+        stream = torch.cuda.current_stream(self.dev).cuda_stream
         out = list(prompt)
         self.last_records = []
         step = 0
         done = False
         while not done:
-            if step <= self.N - 3 or not self.use_cuda_graph:
-                rows = self.lib.lade_step_rows_bound(C.byref(self._lcfg), P, step)
-                if rows < 0:
-                    raise LadeError("lade_step_rows_bound failed")
-                rows = min(rows, self.rows_cap)
-                self.launches += self._launch_step(rows, stream)
-            else:
-                self._steady_graph().replay()
-                self.launches += self._launches_per_graph
+            self.run_forward_step(step, P)
+            if self.DW > 1:
+                self.launches += self._launch_commit(stream)
             rec = self._read_result()
             self.last_records.append(rec)
             out.extend(rec.hits)

@@ -426,3 +426,155 @@ def greedy_lookahead(prompt: Sequence[int], max_new: int, W: int, N: int, G: int
             break
     out_ids = out_ids[:max_length]                                                       # :1221-1225
     return out_ids, steps
+
+
+# --------------------------------------------------------------------------------------------
+# the sampling loop  (lade/decoding.py:137-692), single worker
+# --------------------------------------------------------------------------------------------
+def sample_lookahead(prompt: Sequence[int], max_new: int, W: int, N: int, G: int, model, warper=None,
+                     pool_from_prompt: bool = False, eos_token_id=None, rng: Optional[random.Random] = None,
+                     trace: Optional[list] = None):
+    """Restatement of jacobi_sample_multilevel.  `model` provides step_fn / compact_fn / last_logits
+    (oracle.llama_ref.OracleLlama); `warper(input_ids, scores)` is the HF LogitsProcessorList of
+    temperature / top-k / top-p warpers.  Consumes python `random` and the global torch RNG exactly like the
+    reference (random.random() per accept test :507, torch.multinomial :462,:472,:533,:545, random.choice in
+    filter_window :578-580).  Returns (ids, steps)."""
+    import torch
+
+    rng = rng or random
+    if isinstance(eos_token_id, int):
+        eos_token_id = [eos_token_id]
+    warp = warper if warper is not None else (lambda ids, s: s)
+    GS = N - 1
+    all_old = list(prompt)
+    init_len = len(all_old)
+    out_ids = list(prompt)
+    max_length = init_len + max_new
+
+    def set_token():
+        return rng.choice(all_old)
+
+    past_tokens = [[set_token() for _ in range(W + N - 3)]] + [None] * (N - 2)          # :353
+    fill_level = 0
+    token_map: Dict[int, list] = {}
+    steps = 0
+    lst_token = None
+    if pool_from_prompt:
+        fill_pool_with_prompt(all_old, token_map, N, G)
+    kv_len = 0
+    first = True
+    next_tokens = None
+    eos_t = torch.tensor(eos_token_id) if eos_token_id is not None else None
+    while True:
+        tail = out_ids if first else out_ids[-1:]
+        lst_id = len(out_ids) - 1
+        if past_tokens[N - 2] is not None and lst_token in token_map and G > 0:         # :394
+            guess_tokens = [t for tup in token_map[lst_token] for t in tup]
+        else:
+            guess_tokens = None
+        lay = build_step_layout(tail, lst_id, past_tokens, fill_level, guess_tokens, N, first)
+        _, inp_toks, _ = model.step_fn(lay, kv_len)
+        logits = model.last_logits
+        dev = logits.device
+        if eos_t is not None:
+            eos_t = eos_t.to(dev)
+        input_ids_t = torch.tensor([out_ids], device=dev)
+        steps += 1
+        q, lg = lay.q_len, lay.n_guess_tok
+        kvcache_len = kv_len + lay.n_input
+        step_len = kv_len + q
+        next_token_scores = warp(input_ids_t, logits[lay.n_input - 1:lay.n_input])      # :445
+        max_hit, max_hit_idx = 0, 0
+        if past_tokens[1] is None:                                                       # :458-468
+            probs = torch.nn.functional.softmax(next_token_scores, dim=-1)
+            next_tokens = torch.multinomial(probs, num_samples=1).squeeze(1)
+            hits = [next_tokens.item()]
+            past_tokens[0] = past_tokens[0][1:]
+            past_tokens[1] = list(inp_toks)
+            fill_level += 1
+        elif past_tokens[N - 2] is None:                                                 # :469-480
+            probs = torch.nn.functional.softmax(next_token_scores, dim=-1)
+            next_tokens = torch.multinomial(probs, num_samples=1).squeeze(1)
+            hits = [next_tokens.item()]
+            for level in range(fill_level + 1):
+                past_tokens[level] = past_tokens[level][1:]
+            past_tokens[fill_level + 1] = list(inp_toks)[1:]
+            fill_level += 1
+        else:
+            if guess_tokens is not None:                                                 # :484-540
+                probs_next = torch.nn.functional.softmax(next_token_scores, dim=-1)[0]
+                hits = []
+                guess_logits = warp(input_ids_t, logits[q - lg:])
+                guess_probs = torch.nn.functional.softmax(guess_logits, dim=-1)
+                guess_indices = list(range(lg // GS))
+                for idx_in_ngram in range(GS):
+                    g_idx = 0
+                    is_accept = False
+                    while g_idx < len(guess_indices):
+                        guess_idx = guess_indices[g_idx]
+                        guess_offset = guess_idx * GS
+                        draft_guess = guess_tokens[guess_offset + idx_in_ngram]
+                        prob_accept = min(1, probs_next[draft_guess].item())
+                        sample_prob = rng.random()
+                        if sample_prob < prob_accept:
+                            hits.append(draft_guess)
+                            is_accept = True
+                            max_hit_idx = guess_idx
+                            guess_indices = [gi for gi in guess_indices
+                                             if guess_tokens[gi * GS + idx_in_ngram] == draft_guess]
+                            break
+                        else:
+                            probs_next[draft_guess] = 0
+                            probs_next = probs_next / probs_next.sum()
+                            g_idx += 1
+                    if is_accept:
+                        probs_next = guess_probs[guess_offset + idx_in_ngram]
+                        continue
+                    else:
+                        hits.append(torch.multinomial(probs_next, num_samples=1).item())
+                        break
+                max_hit = len(hits) - 1
+            else:                                                                        # :543-546
+                probs_next = torch.nn.functional.softmax(next_token_scores, dim=-1)
+                next_tokens = torch.multinomial(probs_next, num_samples=1).squeeze(1)
+                hits = [next_tokens.item()]
+            new_results = list(inp_toks)
+            assert len(past_tokens[N - 2]) == W and len(new_results) == W                # :551
+            update_token_map(token_map, lst_token, past_tokens, new_results, N, W, G)    # :553
+            past_tokens[0] = past_tokens[1][1:]
+            for level in range(1, N - 2):
+                past_tokens[level] = past_tokens[level + 1][:]
+            past_tokens[N - 2] = new_results
+            if eos_token_id is not None:                                                 # :578-580
+                for idx in range(len(past_tokens[N - 2])):
+                    if past_tokens[N - 2][idx] == eos_token_id[0]:
+                        past_tokens[N - 2][idx] = set_token()
+        if max_hit > 0:                                                                  # :583-590
+            src = step_len - len(guess_tokens) + max_hit_idx * GS
+            model.compact_fn(kvcache_len, src, max_hit, kvcache_len + max_hit)
+        else:
+            model.compact_fn(kvcache_len, 0, 0, kvcache_len)
+        kv_len = kvcache_len + max_hit
+        lst_token = hits[max_hit]                                                        # :592
+        n_emit = max_hit + 1
+        for hit_ids in range(max_hit + 1):                                               # :594-603
+            if eos_token_id is not None and hits[hit_ids] == eos_token_id[0]:
+                all_old.append(hits[hit_ids])
+                next_tokens = eos_t
+                n_emit = hit_ids + 1
+                break
+            else:
+                all_old.append(hits[hit_ids])
+                if pool_from_prompt:
+                    append_new_generated_pool(all_old[-N:], token_map, N, G)
+        if trace is not None:
+            trace.append(dict(ids=list(lay.ids), hits=list(hits), max_hit=max_hit, max_hit_idx=max_hit_idx,
+                              guess_tokens=list(guess_tokens) if guess_tokens else None))
+        out_ids = out_ids + hits[:n_emit]                                                # :625
+        first = False
+        finished = False
+        if eos_t is not None:                                                            # :636-643
+            finished = bool(next_tokens.to(dev).tile(eos_t.shape[0], 1).ne(eos_t.unsqueeze(1)).prod(dim=0).max() == 0)
+        if finished or len(out_ids) >= max_length:
+            break
+    return out_ids[:max_length], steps
