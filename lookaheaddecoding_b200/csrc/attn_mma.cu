@@ -177,28 +177,35 @@ attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
       }
     }
 
-    // ---- reference rounding + mask
+    // ---- reference rounding + mask (visibility bits built by a rolled loop: keeps the code small)
     const bool need_mask = (col0 + ATT_BN > kv_len);
+    unsigned vbits = 0xffffffffu;   // bit (nt*4 + e) of this thread's 32 score elements
+    if (need_mask) {
+      vbits = 0;
+#pragma unroll 1
+      for (int idx = 0; idx < 32; ++idx) {
+        const int nt = idx >> 2, e = idx & 3;
+        const int col = col0 + nt * 8 + (lane & 3) * 2 + (e & 1);
+        const int r = (e < 2) ? row_a : row_b;
+        const int rd_r = (e < 2) ? rd_a : rd_b;
+        bool vis;
+        if (col < kv_len) vis = true;
+        else if (col >= T) vis = false;
+        else {
+          const int c = col - kv_len;
+          if (is_prefill) vis = (r < q_len) ? (c <= r) : (c == r);
+          else vis = row_sees(rd_r, r, rdp[c], c, level_offset);
+        }
+        vbits |= (vis ? 1u : 0u) << idx;
+      }
+    }
     float mx_a = -INFINITY, mx_b = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         float s = bf16_round(bf16_round(s_acc[nt][e]) * inv_sqrt_d);
-        if (need_mask) {
-          const int col = col0 + nt * 8 + (lane & 3) * 2 + (e & 1);
-          const int r = (e < 2) ? row_a : row_b;
-          const int rd_r = (e < 2) ? rd_a : rd_b;
-          bool vis;
-          if (col < kv_len) vis = true;
-          else if (col >= T) vis = false;
-          else {
-            const int c = col - kv_len;
-            if (is_prefill) vis = (r < q_len) ? (c <= r) : (c == r);
-            else vis = row_sees(rd_r, r, rdp[c], c, level_offset);
-          }
-          if (!vis) s = -INFINITY;
-        }
+        if (!((vbits >> (nt * 4 + e)) & 1u)) s = -INFINITY;
         s_acc[nt][e] = s;
         if (e < 2) mx_a = fmaxf(mx_a, s); else mx_b = fmaxf(mx_b, s);
       }

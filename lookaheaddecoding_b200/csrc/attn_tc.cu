@@ -144,7 +144,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out,
                    const int* __restrict__ rowdesc, const int* __restrict__ meta, float* __restrict__ part_o,
                    float* __restrict__ part_ml, int* __restrict__ counters, int q_pad, int n_heads, int n_kv_heads,
-                   int n_splits, float inv_sqrt_d) {
+                   int n_splits, float inv_sqrt_d, int coop) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int split = blockIdx.x, h = blockIdx.y, mt = blockIdx.z;
   const int q_tiles = gridDim.z;
@@ -420,7 +420,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc_fence_before();
   }
 
-  // ---- teardown + split combine (last CTA of this (head, q tile))
+  // ---- teardown + split combine
   __threadfence();
   __syncthreads();
   if (warp == 1) {
@@ -428,38 +428,78 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tmem_dealloc(tmem_base, 512);
   }
   if (n_active == 1) return;
-  if (threadIdx.x == 0) {
-    const int prev = atomicAdd(&counters[h * q_tiles + mt], 1);
-    *s_flag = (prev == n_active - 1);
+  // Two ways to merge the split partials (m, l, unnormalised O):
+  //   coop  -- every CTA of the (head, q tile) group waits for its siblings and merges 1/n_active of the
+  //            rows: the merge is spread over all SMs.  Needs the whole grid co-resident (host checks
+  //            grid <= #SMs at 1 CTA/SM); the wait is bounded (trap) like every other wait here.
+  //   last  -- the last CTA to arrive merges all rows (any grid size).
+  int* cnt_arrive = &counters[2 * (h * q_tiles + mt)];
+  int* cnt_done = cnt_arrive + 1;
+  int row_lo = 0, row_hi = TC_BM;
+  if (coop) {
+    if (threadIdx.x == 0) {
+      atomicAdd(cnt_arrive, 1);
+      const long long t0 = clock64();
+      while (atomicAdd(cnt_arrive, 0) < n_active) {
+        __nanosleep(32);
+        if (clock64() - t0 > 4000000000LL) __trap();
+      }
+    }
+    const int per = (TC_BM + n_active - 1) / n_active;
+    row_lo = split * per;
+    row_hi = min(TC_BM, row_lo + per);
+  } else {
+    if (threadIdx.x == 0) *s_flag = (atomicAdd(cnt_arrive, 1) == n_active - 1);
+    __syncthreads();
+    if (!*s_flag) return;
   }
   __syncthreads();
-  if (!*s_flag) return;
   __threadfence();
   const int HD = n_heads * TC_D;
   const long long rows_pad = (long long)q_tiles * TC_BM;
-  for (int idx = threadIdx.x; idx < TC_BM * (TC_D / 4); idx += TC_THREADS) {
-    const int rl = idx / (TC_D / 4), c4 = idx % (TC_D / 4);
+  // phase A: per-row merge weights w_s = 2^(m_s - m) / sum_s l_s 2^(m_s - m)  -> smem (Q tile is dead)
+  float* s_w = reinterpret_cast<float*>(smem);
+  for (int rl = row_lo + threadIdx.x; rl < row_hi; rl += TC_THREADS) {
     const int row = mt * TC_BM + rl;
-    if (row >= q_pad) continue;
     float mmax = -INFINITY;
     for (int s = 0; s < n_active; ++s)
       mmax = fmaxf(mmax, __ldcg(part_ml + ((((long long)s * n_heads + h) * rows_pad) + row) * 2));
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float lsum = 0.f;
     for (int s = 0; s < n_active; ++s) {
       const float2 ml = __ldcg(reinterpret_cast<const float2*>(part_ml + ((((long long)s * n_heads + h) * rows_pad) + row) * 2));
       const float wgt = (ml.x == -INFINITY) ? 0.f : exp2f((ml.x - mmax) * TC_LOG2E);
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(part_o + ((((long long)s * n_heads + h) * rows_pad) + row) * TC_D + c4 * 4));
-      acc.x += v.x * wgt; acc.y += v.y * wgt; acc.z += v.z * wgt; acc.w += v.w * wgt;
+      s_w[rl * n_active + s] = wgt;
       lsum += ml.y * wgt;
     }
     const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
+    for (int s = 0; s < n_active; ++s) s_w[rl * n_active + s] *= inv;
+  }
+  __syncthreads();
+  // phase B: out[row] = sum_s w_s O_s[row]; all loads of an item are independent
+  const int n_items = (row_hi - row_lo) * (TC_D / 4);
+  for (int idx = threadIdx.x; idx < n_items; idx += TC_THREADS) {
+    const int rl = row_lo + idx / (TC_D / 4), c4 = idx % (TC_D / 4);
+    const int row = mt * TC_BM + rl;
+    if (row >= q_pad) continue;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int s = 0; s < n_active; ++s) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(part_o + ((((long long)s * n_heads + h) * rows_pad) + row) * TC_D + c4 * 4));
+      const float wgt = s_w[rl * n_active + s];
+      acc.x += v.x * wgt; acc.y += v.y * wgt; acc.z += v.z * wgt; acc.w += v.w * wgt;
+    }
     uint2 pk;
-    pk.x = pack2_bf16(acc.x * inv, acc.y * inv);
-    pk.y = pack2_bf16(acc.z * inv, acc.w * inv);
+    pk.x = pack2_bf16(acc.x, acc.y);
+    pk.y = pack2_bf16(acc.z, acc.w);
     *reinterpret_cast<uint2*>(out + (long long)row * HD + h * TC_D + c4 * 4) = pk;
   }
-  if (threadIdx.x == 0) counters[h * q_tiles + mt] = 0;
+  // counters return to zero once every participant is through
+  if (coop) {
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(cnt_done, 1) == n_active - 1) { *cnt_arrive = 0; *cnt_done = 0; __threadfence(); }
+  } else if (threadIdx.x == 0) {
+    *cnt_arrive = 0;
+  }
 }
 
 // ---- host: tensor maps ----------------------------------------------------------------------------------
@@ -522,7 +562,7 @@ int attn_fwd_tc_launch(cudaStream_t stream, const void* q, const void* k_cache, 
   (void)kv_bound;
   if (head_dim != TC_D) return LADE_EUNSUPPORTED;
   const int q_tiles = (q_pad + TC_BM - 1) / TC_BM;
-  if ((long long)n_heads * q_tiles > TC_MAX_COUNTERS) return LADE_EUNSUPPORTED;
+  if ((long long)n_heads * q_tiles * 2 > TC_MAX_COUNTERS || n_splits > 64) return LADE_EUNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(k_cache) & 15) ||
       (reinterpret_cast<uintptr_t>(v_cache) & 15))
     return LADE_EINVAL;
@@ -541,9 +581,17 @@ int attn_fwd_tc_launch(cudaStream_t stream, const void* q, const void* k_cache, 
   float* part_ml = reinterpret_cast<float*>(counters + TC_MAX_COUNTERS);
   float* part_o = part_ml + (long long)n_splits * n_heads * rows_pad * 2;
   dim3 grid(n_splits, n_heads, q_tiles);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    LADE_CUDA_CHECK(cudaGetDevice(&dev));
+    LADE_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  // cooperative merge only when every CTA of the launch is resident at once (1 CTA/SM kernel)
+  const int coop = ((long long)n_splits * n_heads * q_tiles <= num_sms) ? 1 : 0;
   attn_fwd_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(
       tmQ, tmK, tmV, (__nv_bfloat16*)out, rowdesc, meta, part_o, part_ml, counters, q_pad, n_heads, n_kv_heads, n_splits,
-      1.0f / sqrtf((float)head_dim));
+      1.0f / sqrtf((float)head_dim), coop);
   LADE_LAUNCH_CHECK("attn_fwd_tc_kernel");
   return LADE_OK;
 }

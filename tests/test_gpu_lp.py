@@ -112,7 +112,7 @@ def test_lp_device_state_machine_matches_reference(name):
             check(lib.lade_lp_commit(ctxs[r], stream, recs.data_ptr(), metas[r].data_ptr(), res[r].data_ptr()), "lp_commit")
         rs = [x.cpu().numpy() for x in res]
         for r in range(1, D):
-            np.testing.assert_array_equal(rs[r][:10], rs[0][:10])
+            np.testing.assert_array_equal(rs[r][:9], rs[0][:9])      # slot 9 (n-grams verified) is rank-local
             np.testing.assert_array_equal(rs[r][_cabi.R_HITS:_cabi.R_HITS + GS], rs[0][_cabi.R_HITS:_cabi.R_HITS + GS])
         n_emit = int(rs[0][_cabi.R_N_EMIT])
         out_ids += rs[0][_cabi.R_HITS:_cabi.R_HITS + n_emit].tolist()
