@@ -163,15 +163,23 @@ def attn_roofline(eng, shape, reps=5):
     # weights on a random prompt rarely produce pool hits, so the live decode mostly runs with fewer rows
     W, N, G, GS = eng.W, eng.N, eng.G, eng.GS
     q_len = GS * (W + G)
-    rd = []
-    for r in range(q_len):
-        if r < (N - 1) * W:
-            rd.append((1 << 30) | ((r // W) << 15) | (r % W))            # WINDOW(level, column); a_off = 0
-        else:
-            g = r - (N - 1) * W
-            rd.append((2 << 30) | ((g // GS) << 15) | (g % GS))          # GUESS(n-gram, index)
     import numpy as np
-    rowdesc = torch.from_numpy(np.asarray(rd, dtype=np.uint32).view(np.int32)).to(eng.dev)
+    vis = np.zeros((q_len, q_len), dtype=bool)            # steady lookahead mask, SURVEY App. B (one GPU)
+    for r in range(q_len):
+        if r < GS * W:
+            lvl, j = divmod(r, W)
+            vis[r, : j + 1] = True                        # level-0 block, causal in the column
+            for l2 in range(1, lvl + 1):
+                vis[r, l2 * W + j] = True                 # same column of levels 1..lvl
+        else:
+            e, u = divmod(r - GS * W, GS)
+            vis[r, 0] = True                              # the input token
+            vis[r, GS * W + e * GS: GS * W + e * GS + u + 1] = True
+    mw = (rows + 31) // 32 + 1
+    bits = np.zeros((rows, mw * 32), dtype=bool)
+    bits[:q_len, :q_len] = vis
+    words = np.packbits(bits.reshape(rows, mw, 32), axis=-1, bitorder="little").view(np.uint32).reshape(rows, mw)
+    rowmask = torch.from_numpy(words.view(np.int32).copy()).to(eng.dev)
     meta = torch.zeros(_cabi.META_INTS, dtype=torch.int32, device=eng.dev)
     for k, v in {_cabi.M_Q_LEN: q_len, _cabi.M_KV_LEN: kv_len, _cabi.M_N_INPUT: 1, _cabi.M_TINY: W,
                  _cabi.M_N_LEVELS: N - 1, _cabi.M_N_GUESS_TOK: G * GS, _cabi.M_PHASE: 2, _cabi.M_Q_PAD: rows}.items():
@@ -182,7 +190,7 @@ def attn_roofline(eng, shape, reps=5):
     def one_pass():
         for l in range(eng.L):
             _cabi.check(lib.lade_attn_fwd(stream.cuda_stream, qb.data_ptr(), eng.kv[l, 0].data_ptr(), eng.kv[l, 1].data_ptr(),
-                                          eng.attn_out.data_ptr(), rowdesc.data_ptr(), meta.data_ptr(),
+                                          eng.attn_out.data_ptr(), rowmask.data_ptr(), mw, meta.data_ptr(),
                                           eng.attn_scratch.data_ptr(), rows, eng.nh, eng.nkv, eng.D, eng.kv_capacity,
                                           eng.kv_capacity, eng.attn_splits, eng.attn_impl))
     for _ in range(3):

@@ -20,7 +20,7 @@
  *   KV cache of one layer : K and V each [n_kv_heads][kv_capacity][head_dim] bf16
  *   Q (post-RoPE)         : [n_heads][q_pad][head_dim] bf16
  *   attention output      : [q_rows][n_heads*head_dim] bf16
- *   step rows             : ids/pos/rowdesc int32 [q_pad]
+ *   step rows             : ids/pos/rowdesc int32 [q_pad] ; rowmask uint32 [q_pad][mask_words]
  *   step meta             : int32 [LADE_META_INTS] (indices LADE_M_*)
  *   lm rows / argmax slots: int32 [lm_cap], lm_cap = 1 + (W+N-3) + G*(N-1):
  *                             slot 0 = row predicting the next token, slots [1, 1+W+N-3) = rows of the
@@ -119,9 +119,12 @@ int lade_ctx_reset(LadeCtx* ctx, void* stream, const int32_t* prompt_host, int32
  * the lm_head row list and the step meta record.  `q_pad` rows are written (rows past the live count
  * are PAD rows).  Replaces LlamaForCausalLM.jforward_multilevel's input assembly
  * (lade/models/modeling_llama.py:1458-1511), the pool lookup of lade/decoding.py:948-954 and the
- * scalar part of j_make_causal_mask_multilevel (modeling_llama.py:132-138). */
+ * mask of j_make_causal_mask_multilevel (modeling_llama.py:115-207) in its compact forms: one class
+ * descriptor per row (`rowdesc`) and, for non-prefill steps, the visibility bitmask of the step block
+ * (`rowmask`, bit c of row r = row r attends step column c; mask_words >= ceil(q_pad/32)). */
 int lade_step_layout(LadeCtx* ctx, void* stream, int32_t q_pad, int32_t* ids_out, int32_t* pos_out,
-                     int32_t* rowdesc_out, int32_t* lm_rows_out, int32_t* meta_out);
+                     int32_t* rowdesc_out, int32_t* lm_rows_out, int32_t* meta_out,
+                     uint32_t* rowmask_out /* [q_pad][mask_words], nullable */, int32_t mask_words);
 
 /* Expected live row count of the upcoming step as a pure function of the step index (host side, no
  * sync): prefill = P + W+N-3 ; fill step k ; steady = (N-1)*(W+G).  Returns the count or <0. */
@@ -149,12 +152,12 @@ int lade_rope_append(void* stream, const void* qkv, const void* cos_tab, const v
                      int32_t kv_capacity, int32_t max_pos);
 
 /* Lookahead attention over the persistent KV cache (the roofline kernel).  softmax(QK^T/sqrt(D) +
- * lookahead mask) V with the mask evaluated in registers from `rowdesc`/`meta`; all step rows see the
- * committed cache.  Replaces LlamaAttention.forward's attention core (modeling_llama.py:520-541), the
+ * lookahead mask) V with the mask bits of `rowmask` tested in registers (prefill steps: plain causal,
+ * rowmask unused); all step rows see the committed cache.  Replaces LlamaAttention.forward's attention core (modeling_llama.py:520-541), the
  * dense mask of j_make_causal_mask_multilevel (:115-207) and flash_attn_lade.flash_attn_func(...,
  * lookahead=[...]) (:705-713).  `scratch` holds split-KV partials: lade_attn_scratch_bytes(). */
 int lade_attn_fwd(void* stream, const void* q, const void* k_cache, const void* v_cache, void* out,
-                  const int32_t* rowdesc, const int32_t* meta, void* scratch, int32_t q_pad,
+                  const uint32_t* rowmask, int32_t mask_words, const int32_t* meta, void* scratch, int32_t q_pad,
                   int32_t n_heads, int32_t n_kv_heads, int32_t head_dim, int32_t kv_capacity,
                   int32_t kv_bound /* host upper bound of kv_len + q_len */, int32_t n_splits,
                   int32_t impl /* 0 = default (= 2), 1 = mma.sync path, 2 = tcgen05/TMA path */);

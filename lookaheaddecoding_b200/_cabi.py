@@ -38,12 +38,12 @@ _SIGNATURES = {
     "lade_ctx_create": (C.c_int, [C.POINTER(LadeConfig), C.POINTER(c_p)]),
     "lade_ctx_destroy": (C.c_int, [c_p]),
     "lade_ctx_reset": (C.c_int, [c_p, c_p, c_p, c_i32, c_p, c_i32, c_i32]),
-    "lade_step_layout": (C.c_int, [c_p, c_p, c_i32, c_p, c_p, c_p, c_p, c_p]),
+    "lade_step_layout": (C.c_int, [c_p, c_p, c_i32, c_p, c_p, c_p, c_p, c_p, c_p, c_i32]),
     "lade_step_rows_bound": (C.c_int, [C.POINTER(LadeConfig), c_i32, c_i32]),
     "lade_rmsnorm": (C.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, C.c_float]),
     "lade_rmsnorm_gather": (C.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_i32, C.c_float]),
     "lade_rope_append": (C.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p] + [c_i32] * 7),
-    "lade_attn_fwd": (C.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p] + [c_i32] * 8),
+    "lade_attn_fwd": (C.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_p, c_p] + [c_i32] * 8),
     "lade_attn_scratch_bytes": (C.c_int64, [c_i32, c_i32, c_i32, c_i32]),
     "lade_swiglu": (C.c_int, [c_p, c_p, c_p, c_i32, c_i32]),
     "lade_argmax_rows": (C.c_int, [c_p, c_p, c_i32, c_i32, c_i32, c_p]),

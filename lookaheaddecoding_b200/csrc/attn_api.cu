@@ -3,10 +3,10 @@
 
 namespace lade {
 int attn_fwd_mma_launch(cudaStream_t stream, const void* q, const void* k_cache, const void* v_cache, void* out,
-                        const int32_t* rowdesc, const int32_t* meta, void* scratch, int q_pad, int n_heads,
+                        const uint32_t* rowmask, int mask_words, const int32_t* meta, void* scratch, int q_pad, int n_heads,
                         int n_kv_heads, int head_dim, int kv_capacity, int n_splits);
 int attn_fwd_tc_launch(cudaStream_t stream, const void* q, const void* k_cache, const void* v_cache, void* out,
-                       const int32_t* rowdesc, const int32_t* meta, void* scratch, int q_pad, int n_heads,
+                       const uint32_t* rowmask, int mask_words, const int32_t* meta, void* scratch, int q_pad, int n_heads,
                        int n_kv_heads, int head_dim, int kv_capacity, int kv_bound, int n_splits);
 }  // namespace lade
 
@@ -19,16 +19,17 @@ int64_t lade_attn_scratch_bytes(int32_t q_pad, int32_t n_heads, int32_t head_dim
 }
 
 int lade_attn_fwd(void* stream, const void* q, const void* k_cache, const void* v_cache, void* out,
-                  const int32_t* rowdesc, const int32_t* meta, void* scratch, int32_t q_pad,
+                  const uint32_t* rowmask, int32_t mask_words, const int32_t* meta, void* scratch, int32_t q_pad,
                   int32_t n_heads, int32_t n_kv_heads, int32_t head_dim, int32_t kv_capacity,
                   int32_t kv_bound, int32_t n_splits, int32_t impl) {
-  if (!q || !k_cache || !v_cache || !out || !rowdesc || !meta || !scratch) return LADE_EINVAL;
+  if (!q || !k_cache || !v_cache || !out || !meta || !scratch) return LADE_EINVAL;
+  if (rowmask && mask_words * 32 < q_pad) return LADE_EINVAL;   // rowmask may be NULL for prefill-only use
   if (q_pad < 1 || n_heads < 1 || n_kv_heads < 1 || n_heads % n_kv_heads != 0 || n_splits < 1 || kv_capacity < 1)
     return LADE_EINVAL;
   if (impl == 0 || impl == 2)   // default: the Blackwell-native tcgen05/TMA kernel
-    return lade::attn_fwd_tc_launch((cudaStream_t)stream, q, k_cache, v_cache, out, rowdesc, meta, scratch, q_pad,
+    return lade::attn_fwd_tc_launch((cudaStream_t)stream, q, k_cache, v_cache, out, rowmask, mask_words, meta, scratch, q_pad,
                                     n_heads, n_kv_heads, head_dim, kv_capacity, kv_bound, n_splits);
-  return lade::attn_fwd_mma_launch((cudaStream_t)stream, q, k_cache, v_cache, out, rowdesc, meta, scratch, q_pad,
+  return lade::attn_fwd_mma_launch((cudaStream_t)stream, q, k_cache, v_cache, out, rowmask, mask_words, meta, scratch, q_pad,
                                    n_heads, n_kv_heads, head_dim, kv_capacity, n_splits);
 }
 

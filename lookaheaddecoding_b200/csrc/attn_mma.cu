@@ -70,13 +70,13 @@ __device__ __forceinline__ void load_tile_async(__nv_bfloat16* sK, __nv_bfloat16
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k_cache,
                     const __nv_bfloat16* __restrict__ v_cache, __nv_bfloat16* __restrict__ out,
-                    const int* __restrict__ rowdesc, const int* __restrict__ meta, float* __restrict__ part_o,
+                    const uint32_t* __restrict__ rowmask, int mask_words, const int* __restrict__ meta,
+                    float* __restrict__ part_o,
                     float* __restrict__ part_ml, int* __restrict__ counters, int q_pad, int n_heads,
                     int n_kv_heads, int kv_capacity, int n_splits, float inv_sqrt_d) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_raw);
   __nv_bfloat16* sV = sK + ATT_STAGES * ATT_BN * ATT_D;
-  int* s_rd = reinterpret_cast<int*>(sV + ATT_STAGES * ATT_BN * ATT_D);
   __shared__ int s_last;
 
   const int split = blockIdx.x, h = blockIdx.y, mt = blockIdx.z;
@@ -85,7 +85,6 @@ attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
   const int q_len = meta[LADE_M_Q_LEN];
   const int kv_len = meta[LADE_M_KV_LEN];
   const int is_prefill = meta[LADE_M_IS_PREFILL];
-  const int level_offset = meta[LADE_M_LEVEL_OFFSET];
   const int T = kv_len + q_len;
   int Tm = T;
   if (is_prefill) {  // causal: rows of this q tile see nothing past their own column
@@ -112,12 +111,6 @@ attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
     cp_async_commit();
   }
 
-  // row descriptors of the step columns (non-prefill steps are short: (N-1)*(W+G) rows)
-  const bool rd_in_smem = (!is_prefill) && q_len <= ATT_RD_SMEM;
-  if (rd_in_smem)
-    for (int i = threadIdx.x; i < q_len; i += ATT_THREADS) s_rd[i] = rowdesc[i];
-  const int* rdp = rd_in_smem ? s_rd : rowdesc;
-
   // Q fragments (A operand), 16 rows per warp
   const int row_a = mt * ATT_BM + warp * 16 + (lane >> 2);  // step-local row of c0/c1
   const int row_b = row_a + 8;
@@ -133,8 +126,9 @@ attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
       qf[kk][3] = row_b < q_pad ? *reinterpret_cast<const unsigned*>(qh + (long long)row_b * ATT_D + col + 8) : 0u;
     }
   }
-  const int rd_a = row_a < q_pad ? rowdesc[row_a] : rowdesc_make(LADE_ROW_PAD, 0, 0);
-  const int rd_b = row_b < q_pad ? rowdesc[row_b] : rowdesc_make(LADE_ROW_PAD, 0, 0);
+  const bool have_mask = (!is_prefill) && rowmask != nullptr;
+  const uint32_t* mrow_a = (have_mask && row_a < q_pad) ? rowmask + (long long)row_a * mask_words : nullptr;
+  const uint32_t* mrow_b = (have_mask && row_b < q_pad) ? rowmask + (long long)row_b * mask_words : nullptr;
 
   float o_acc[16][4];
 #pragma unroll
@@ -177,35 +171,25 @@ attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
       }
     }
 
-    // ---- reference rounding + mask (visibility bits built by a rolled loop: keeps the code small)
+    // ---- reference rounding + mask: 64 visibility bits per row for this tile, tested in registers
     const bool need_mask = (col0 + ATT_BN > kv_len);
-    unsigned vbits = 0xffffffffu;   // bit (nt*4 + e) of this thread's 32 score elements
+    unsigned long long va = ~0ull, vb = ~0ull;
     if (need_mask) {
-      vbits = 0;
-#pragma unroll 1
-      for (int idx = 0; idx < 32; ++idx) {
-        const int nt = idx >> 2, e = idx & 3;
-        const int col = col0 + nt * 8 + (lane & 3) * 2 + (e & 1);
-        const int r = (e < 2) ? row_a : row_b;
-        const int rd_r = (e < 2) ? rd_a : rd_b;
-        bool vis;
-        if (col < kv_len) vis = true;
-        else if (col >= T) vis = false;
-        else {
-          const int c = col - kv_len;
-          if (is_prefill) vis = (r < q_len) ? (c <= r) : (c == r);
-          else vis = row_sees(rd_r, r, rdp[c], c, level_offset);
-        }
-        vbits |= (vis ? 1u : 0u) << idx;
-      }
+      va = (unsigned long long)visible_bits32(mrow_a, mask_words, col0, kv_len, q_len, is_prefill, row_a) |
+           ((unsigned long long)visible_bits32(mrow_a, mask_words, col0 + 32, kv_len, q_len, is_prefill, row_a) << 32);
+      vb = (unsigned long long)visible_bits32(mrow_b, mask_words, col0, kv_len, q_len, is_prefill, row_b) |
+           ((unsigned long long)visible_bits32(mrow_b, mask_words, col0 + 32, kv_len, q_len, is_prefill, row_b) << 32);
     }
+    va >>= (lane & 3) * 2;   // this thread's two columns of every 8-wide n-tile
+    vb >>= (lane & 3) * 2;
     float mx_a = -INFINITY, mx_b = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         float s = bf16_round(bf16_round(s_acc[nt][e]) * inv_sqrt_d);
-        if (!((vbits >> (nt * 4 + e)) & 1u)) s = -INFINITY;
+        const unsigned long long vv = (e < 2) ? va : vb;
+        if (!((vv >> (nt * 8 + (e & 1))) & 1ull)) s = -INFINITY;
         s_acc[nt][e] = s;
         if (e < 2) mx_a = fmaxf(mx_a, s); else mx_b = fmaxf(mx_b, s);
       }
@@ -334,11 +318,11 @@ attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
 }
 
 int attn_fwd_mma_launch(cudaStream_t stream, const void* q, const void* k_cache, const void* v_cache, void* out,
-                        const int32_t* rowdesc, const int32_t* meta, void* scratch, int q_pad, int n_heads,
+                        const uint32_t* rowmask, int mask_words, const int32_t* meta, void* scratch, int q_pad, int n_heads,
                         int n_kv_heads, int head_dim, int kv_capacity, int n_splits) {
   if (head_dim != ATT_D) return LADE_EUNSUPPORTED;
   const int q_tiles = (q_pad + ATT_BM - 1) / ATT_BM;
-  const size_t smem = (size_t)2 * ATT_STAGES * ATT_BN * ATT_D * sizeof(__nv_bfloat16) + ATT_RD_SMEM * sizeof(int);
+  const size_t smem = (size_t)2 * ATT_STAGES * ATT_BN * ATT_D * sizeof(__nv_bfloat16);
   static bool attr_set = false;
   if (!attr_set) {
     LADE_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -353,7 +337,7 @@ int attn_fwd_mma_launch(cudaStream_t stream, const void* q, const void* k_cache,
   dim3 grid(n_splits, n_heads, q_tiles);
   attn_fwd_mma_kernel<<<grid, ATT_THREADS, smem, stream>>>(
       (const __nv_bfloat16*)q, (const __nv_bfloat16*)k_cache, (const __nv_bfloat16*)v_cache, (__nv_bfloat16*)out,
-      rowdesc, meta, part_o, part_ml, counters, q_pad, n_heads, n_kv_heads, kv_capacity, n_splits,
+      rowmask, mask_words, meta, part_o, part_ml, counters, q_pad, n_heads, n_kv_heads, kv_capacity, n_splits,
       1.0f / sqrtf((float)head_dim));
   LADE_LAUNCH_CHECK("attn_fwd_mma_kernel");
   return LADE_OK;

@@ -5,8 +5,9 @@
 //   warp 0      TMA producer   Q tile + a STAGES-deep ring of K/V tiles (128 kv rows x 128 d, SWIZZLE_128B)
 //   warp 1      MMA issuer     S = Q K^T  (kind::f16, M=128 N=128 K=16 x8, both operands K-major)
 //                              O += P V   (A = P K-major from smem, B = V MN-major from smem), TMEM alloc
-//   warps 2..5  softmax        tcgen05.ld S row -> reference rounding -> lookahead mask in registers ->
-//                              exp2 -> P (bf16, swizzled into the K tile's smem) ; lazy O rescale in TMEM
+//   warps 2..9  softmax        two threads per query row (TMEM lane), each owning 64 of the tile's 128 kv
+//                              columns: tcgen05.ld -> reference rounding -> lookahead mask bits in registers
+//                              -> exp2 -> P (bf16, swizzled into the K tile's smem) ; lazy O rescale in TMEM
 // TMEM: S double buffer (2 x 128 cols) + O (128 cols).
 //
 // Numerics follow attn_mma.cu / the reference (lade/models/modeling_llama.py:520-541); the mask is the
@@ -24,13 +25,13 @@ constexpr int TC_BM = 128;
 constexpr int TC_BN = 128;
 constexpr int TC_D = 128;
 constexpr int TC_STAGES = 3;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;
 constexpr int TC_TILE_BYTES = 128 * 128 * 2;   // one [128 x 128] bf16 tile = two [128 x 64] swizzle blocks
 constexpr int TC_HALF_BYTES = TC_TILE_BYTES / 2;
-constexpr int TC_RD_SMEM = 512;
+constexpr int TC_XCH_FLOATS = 512;   // row-max / row-sum exchange between the two column halves
 constexpr int TC_MAX_COUNTERS = 16384;
 constexpr int TC_SMEM_TILES = TC_TILE_BYTES * (1 + 2 * TC_STAGES);
-constexpr int TC_SMEM_BYTES = TC_SMEM_TILES + 256 + TC_RD_SMEM * 4;
+constexpr int TC_SMEM_BYTES = TC_SMEM_TILES + 256 + TC_XCH_FLOATS * 4;
 constexpr float TC_LOG2E = 1.4426950408889634f;
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------
@@ -133,6 +134,14 @@ __host__ __device__ constexpr uint32_t umma_idesc(bool b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
+}
 __device__ __forceinline__ unsigned pack2_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<unsigned*>(&v);
@@ -142,7 +151,8 @@ __device__ __forceinline__ unsigned pack2_bf16(float lo, float hi) {
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out,
-                   const int* __restrict__ rowdesc, const int* __restrict__ meta, float* __restrict__ part_o,
+                   const uint32_t* __restrict__ rowmask, int mask_words, const int* __restrict__ meta,
+                   float* __restrict__ part_o,
                    float* __restrict__ part_ml, int* __restrict__ counters, int q_pad, int n_heads, int n_kv_heads,
                    int n_splits, float inv_sqrt_d, int coop) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -153,7 +163,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int q_len = meta[LADE_M_Q_LEN];
   const int kv_len = meta[LADE_M_KV_LEN];
   const int is_prefill = meta[LADE_M_IS_PREFILL];
-  const int level_offset = meta[LADE_M_LEVEL_OFFSET];
   const int T = kv_len + q_len;
   int Tm = T;
   if (is_prefill) Tm = min(T, kv_len + min(q_len, (mt + 1) * TC_BM));
@@ -174,7 +183,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             B_SFULL = 1 + 3 * TC_STAGES, B_PFULL = 3 + 3 * TC_STAGES, B_OFINAL = 5 + 3 * TC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   int* s_flag = reinterpret_cast<int*>(bars + 25);
-  int* s_rd = reinterpret_cast<int*>(smem + TC_SMEM_TILES + 256);
+  float* s_xch = reinterpret_cast<float*>(smem + TC_SMEM_TILES + 256);
   const uint32_t sQ_a = smem_u32(sQ);
   auto sK_a = [&](int s) { return sQ_a + (uint32_t)TC_TILE_BYTES * (1 + 2 * s); };
   auto sV_a = [&](int s) { return sQ_a + (uint32_t)TC_TILE_BYTES * (2 + 2 * s); };
@@ -183,15 +192,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if ((sQ_a & 1023u) != 0) __trap();   // SWIZZLE_128B tiles need 1024-byte alignment
     mbar_init(BAR(B_QFULL), 1);
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(BAR(B_KFULL + s), 1); mbar_init(BAR(B_VFULL + s), 1); mbar_init(BAR(B_FREE + s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(BAR(B_SFULL + b), 1); mbar_init(BAR(B_PFULL + b), 128); }
+    for (int b = 0; b < 2; ++b) { mbar_init(BAR(B_SFULL + b), 1); mbar_init(BAR(B_PFULL + b), 256); }
     mbar_init(BAR(B_OFINAL), 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
-  const bool rd_in_smem = (!is_prefill) && q_len <= TC_RD_SMEM;
-  if (rd_in_smem && warp >= 2)
-    for (int i = threadIdx.x - 64; i < q_len; i += 128) s_rd[i] = rowdesc[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -256,57 +262,46 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else {
-    // ================= softmax: one thread per query row =================
-    // Code size matters here (the instruction cache is 32 KB): S is consumed in 32-column chunks by rolled
-    // loops, in two passes over TMEM (row max, then exp/P) instead of holding 128 scores in registers.
+    // ================= softmax: two threads per query row =================
+    // Warp w (2..9): TMEM quadrant (w & 3) = rows, column half (w - 2) >> 2 = kv columns [64*half, 64*half+64)
+    // of every tile.  The halves meet once per tile (row max) through smem + a named barrier.  Code size
+    // matters (32 KB instruction cache): 32-column chunks, rolled loops, two passes over TMEM.
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row_l = quad * 32 + lane;             // TMEM lane == row inside the tile
     const int row = mt * TC_BM + row_l;             // step-local row
-    const int rd_r = row < q_pad ? rowdesc[row] : rowdesc_make(LADE_ROW_PAD, 0, 0);
-    const int* rdp = rd_in_smem ? s_rd : rowdesc;
+    const uint32_t* mrow = (row < q_pad && !is_prefill && rowmask != nullptr) ? rowmask + (long long)row * mask_words : nullptr;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     float m_used = -INFINITY, l_sum = 0.f;
     for (int j = 0; j < my_tiles; ++j) {
       const int buf = j & 1, s = j % TC_STAGES;
       mbar_wait(BAR(B_SFULL + buf), (j >> 1) & 1);
       tc_fence_after();
-      const uint32_t ts = tmem_base + lane_addr + (uint32_t)buf * 128u;
-      const int col0 = (tile_lo + j) * TC_BN;
-      // visibility bits of this row for the 128 columns of the tile (all ones for pure-cache tiles)
-      uint32_t mb0 = 0xffffffffu, mb1 = 0xffffffffu, mb2 = 0xffffffffu, mb3 = 0xffffffffu;
-      if (col0 + TC_BN > kv_len) {
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t bits = 0;
-#pragma unroll 1
-          for (int i = 0; i < 32; ++i) {
-            const int col = col0 + c * 32 + i;
-            bool vis;
-            if (col < kv_len) vis = true;
-            else if (col >= T) vis = false;
-            else {
-              const int cc = col - kv_len;
-              if (is_prefill) vis = (row < q_len) ? (cc <= row) : (cc == row);
-              else vis = row_sees(rd_r, row, rdp[cc], cc, level_offset);
-            }
-            bits |= (vis ? 1u : 0u) << i;
-          }
-          if (c == 0) mb0 = bits; else if (c == 1) mb1 = bits; else if (c == 2) mb2 = bits; else mb3 = bits;
-        }
+      const uint32_t ts = tmem_base + lane_addr + (uint32_t)buf * 128u + (uint32_t)half * 64u;
+      const int col0 = (tile_lo + j) * TC_BN + half * 64;
+      const bool need_mask = (col0 + 64 > kv_len);
+      uint32_t mb0 = 0xffffffffu, mb1 = 0xffffffffu;
+      if (need_mask) {
+        mb0 = visible_bits32(mrow, mask_words, col0, kv_len, q_len, is_prefill, row);
+        mb1 = visible_bits32(mrow, mask_words, col0 + 32, kv_len, q_len, is_prefill, row);
       }
-      // pass 1: row max.  bf16 rounding and the positive scale are monotone, so round the max once.
+      // pass 1: row max of my 64 columns.  bf16 rounding and the positive scale are monotone: round once.
       float mx_raw = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         float v[32];
         tmem_ld32(ts + c * 32, v);
         tmem_ld_wait();
-        const uint32_t mb = c == 0 ? mb0 : (c == 1 ? mb1 : (c == 2 ? mb2 : mb3));
+        const uint32_t mb = c == 0 ? mb0 : mb1;
 #pragma unroll
         for (int i = 0; i < 32; ++i) mx_raw = fmaxf(mx_raw, ((mb >> i) & 1u) ? v[i] : -INFINITY);
       }
+      float* xch = s_xch + (j & 1) * 256;            // slot parity: no write-after-read race across tiles
+      xch[half * 128 + row_l] = mx_raw;
+      named_bar_sync(1, 256);
+      mx_raw = fmaxf(mx_raw, xch[(half ^ 1) * 128 + row_l]);
       const float mx = (mx_raw == -INFINITY) ? -INFINITY : bf16_round(bf16_round(mx_raw) * inv_sqrt_d);
-      // lazy rescale: keep the stale max while it is within 2^8 of the running max
+      // lazy rescale: keep the stale max while it is within 2^8 of the running max (both halves agree)
       if (j == 0) {
         m_used = mx;
       } else {
@@ -318,13 +313,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const float scale = (m_new == -INFINITY) ? 1.f : exp2f((m_used - m_new) * TC_LOG2E);
           l_sum *= scale;
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < 2; ++c) {              // my half of the O columns
             float ov[32];
-            tmem_ld32(tmem_O + lane_addr + c * 32, ov);
+            tmem_ld32(tmem_O + lane_addr + half * 64 + c * 32, ov);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) ov[i] *= scale;
-            tmem_st32(tmem_O + lane_addr + c * 32, ov);
+            tmem_st32(tmem_O + lane_addr + half * 64 + c * 32, ov);
           }
           tmem_st_wait();
           m_used = m_new;
@@ -332,16 +327,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       const float off = (m_used == -INFINITY) ? 0.f : m_used * TC_LOG2E;
       // pass 2: P = exp2(score - max) as bf16 into the K stage, K-major SWIZZLE_128B:
-      //         [kv block of 64][row][128 B], 16-byte chunk index ^ (row & 7)
-      unsigned char* pK = smem + TC_TILE_BYTES * (1 + 2 * s);
+      //         [kv block of 64 = my half][row][128 B], 16-byte chunk index ^ (row & 7)
+      unsigned char* prow = smem + TC_TILE_BYTES * (1 + 2 * s) + half * TC_HALF_BYTES + row_l * 128;
       float psum = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         float v[32];
         tmem_ld32(ts + c * 32, v);
         tmem_ld_wait();
-        const uint32_t mb = c == 0 ? mb0 : (c == 1 ? mb1 : (c == 2 ? mb2 : mb3));
-        unsigned char* prow = pK + (c >> 1) * TC_HALF_BYTES + row_l * 128;
+        const uint32_t mb = c == 0 ? mb0 : mb1;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float p[8];
@@ -349,28 +343,26 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int e = 0; e < 8; ++e) {
             const int i = g * 8 + e;
             const float x = bf16_round(bf16_round(v[i]) * inv_sqrt_d);        // reference rounding points
-            p[e] = ((mb >> i) & 1u) ? exp2f(x * TC_LOG2E - off) : 0.f;
+            p[e] = ((mb >> i) & 1u) ? ex2_approx(x * TC_LOG2E - off) : 0.f;
             psum += p[e];
           }
           uint4 pk;
           pk.x = pack2_bf16(p[0], p[1]); pk.y = pack2_bf16(p[2], p[3]);
           pk.z = pack2_bf16(p[4], p[5]); pk.w = pack2_bf16(p[6], p[7]);
-          const int cc = (c & 1) * 4 + g;
+          const int cc = c * 4 + g;
           *reinterpret_cast<uint4*>(prow + ((cc ^ (row_l & 7)) << 4)) = pk;
         }
       }
       l_sum += psum;
       // stale cache rows past T must not reach the PV MMA (0 * NaN): zero them in the staged V tile
-      if (col0 + TC_BN > T) {
+      const int tile0 = (tile_lo + j) * TC_BN;
+      if (tile0 + TC_BN > T) {
         mbar_wait(BAR(B_VFULL + s), (j / TC_STAGES) & 1);
-        if (col0 + row_l >= T) {
-          unsigned char* pV = smem + TC_TILE_BYTES * (2 + 2 * s);
+        if (tile0 + row_l >= T) {                   // V tile row == kv row; each half clears one d block
+          unsigned char* pV = smem + TC_TILE_BYTES * (2 + 2 * s) + half * TC_HALF_BYTES + row_l * 128;
           const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll 1
-          for (int cc = 0; cc < 8; ++cc) {
-            *reinterpret_cast<uint4*>(pV + row_l * 128 + cc * 16) = z;
-            *reinterpret_cast<uint4*>(pV + TC_HALF_BYTES + row_l * 128 + cc * 16) = z;
-          }
+          for (int cc = 0; cc < 8; ++cc) *reinterpret_cast<uint4*>(pV + cc * 16) = z;
         }
       }
       fence_proxy_async();
@@ -378,20 +370,24 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_arrive(BAR(B_PFULL + buf));
     }
 
-    // ---- epilogue: O (TMEM) -> final output or split partial
+    // ---- epilogue: O (TMEM) -> final output or split partial; each half owns 64 of the 128 d columns
     mbar_wait(BAR(B_OFINAL), 0);
     tc_fence_after();
+    named_bar_sync(1, 256);                          // s_xch is free again
+    s_xch[half * 128 + row_l] = l_sum;
+    named_bar_sync(1, 256);
+    l_sum += s_xch[(half ^ 1) * 128 + row_l];
     const int HD = n_heads * TC_D;
     const long long rows_pad = (long long)q_tiles * TC_BM;
     if (n_active == 1) {
       const float inv = l_sum > 0.f ? 1.f / l_sum : 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         float ov[32];
-        tmem_ld32(tmem_O + lane_addr + c * 32, ov);
+        tmem_ld32(tmem_O + lane_addr + half * 64 + c * 32, ov);
         tmem_ld_wait();
         if (row < q_pad) {
-          uint4* dst = reinterpret_cast<uint4*>(out + (long long)row * HD + h * TC_D + c * 32);
+          uint4* dst = reinterpret_cast<uint4*>(out + (long long)row * HD + h * TC_D + half * 64 + c * 32);
 #pragma unroll
           for (int v4 = 0; v4 < 4; ++v4) {
             uint4 pk;
@@ -404,24 +400,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
     } else {
-      float* po = part_o + (((long long)split * n_heads + h) * rows_pad + row) * TC_D;
+      float* po = part_o + (((long long)split * n_heads + h) * rows_pad + row) * TC_D + half * 64;
       float* pml = part_ml + (((long long)split * n_heads + h) * rows_pad + row) * 2;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         float ov[32];
-        tmem_ld32(tmem_O + lane_addr + c * 32, ov);
+        tmem_ld32(tmem_O + lane_addr + half * 64 + c * 32, ov);
         tmem_ld_wait();
 #pragma unroll
         for (int v4 = 0; v4 < 8; ++v4)
           reinterpret_cast<float4*>(po + c * 32)[v4] = make_float4(ov[v4 * 4], ov[v4 * 4 + 1], ov[v4 * 4 + 2], ov[v4 * 4 + 3]);
       }
-      *reinterpret_cast<float2*>(pml) = make_float2(m_used, l_sum);
+      if (half == 0) *reinterpret_cast<float2*>(pml) = make_float2(m_used, l_sum);
     }
     tc_fence_before();
   }
 
   // ---- teardown + split combine
-  __threadfence();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -438,6 +433,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   int row_lo = 0, row_hi = TC_BM;
   if (coop) {
     if (threadIdx.x == 0) {
+      __threadfence();                               // publish this CTA's partials (cumulative over the barrier)
       atomicAdd(cnt_arrive, 1);
       const long long t0 = clock64();
       while (atomicAdd(cnt_arrive, 0) < n_active) {
@@ -449,12 +445,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     row_lo = split * per;
     row_hi = min(TC_BM, row_lo + per);
   } else {
-    if (threadIdx.x == 0) *s_flag = (atomicAdd(cnt_arrive, 1) == n_active - 1);
+    if (threadIdx.x == 0) {
+      __threadfence();
+      *s_flag = (atomicAdd(cnt_arrive, 1) == n_active - 1);
+    }
     __syncthreads();
     if (!*s_flag) return;
   }
   __syncthreads();
-  __threadfence();
   const int HD = n_heads * TC_D;
   const long long rows_pad = (long long)q_tiles * TC_BM;
   // phase A: per-row merge weights w_s = 2^(m_s - m) / sum_s l_s 2^(m_s - m)  -> smem (Q tile is dead)
@@ -557,12 +555,13 @@ static int get_tensor_map(const void* ptr, int rows, int heads, CUtensorMap* out
 }
 
 int attn_fwd_tc_launch(cudaStream_t stream, const void* q, const void* k_cache, const void* v_cache, void* out,
-                       const int32_t* rowdesc, const int32_t* meta, void* scratch, int q_pad, int n_heads,
+                       const uint32_t* rowmask, int mask_words, const int32_t* meta, void* scratch, int q_pad, int n_heads,
                        int n_kv_heads, int head_dim, int kv_capacity, int kv_bound, int n_splits) {
   (void)kv_bound;
   if (head_dim != TC_D) return LADE_EUNSUPPORTED;
   const int q_tiles = (q_pad + TC_BM - 1) / TC_BM;
-  if ((long long)n_heads * q_tiles * 2 > TC_MAX_COUNTERS || n_splits > 64) return LADE_EUNSUPPORTED;
+  if ((long long)n_heads * q_tiles * 2 > TC_MAX_COUNTERS) return LADE_EUNSUPPORTED;
+  if (n_splits > 64) n_splits = 64;   // merge weights live in the 32 KB Q tile: 128 rows x 64 splits
   if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(k_cache) & 15) ||
       (reinterpret_cast<uintptr_t>(v_cache) & 15))
     return LADE_EINVAL;
@@ -590,7 +589,7 @@ int attn_fwd_tc_launch(cudaStream_t stream, const void* q, const void* k_cache, 
   // cooperative merge only when every CTA of the launch is resident at once (1 CTA/SM kernel)
   const int coop = ((long long)n_splits * n_heads * q_tiles <= num_sms) ? 1 : 0;
   attn_fwd_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(
-      tmQ, tmK, tmV, (__nv_bfloat16*)out, rowdesc, meta, part_o, part_ml, counters, q_pad, n_heads, n_kv_heads, n_splits,
+      tmQ, tmK, tmV, (__nv_bfloat16*)out, rowmask, mask_words, meta, part_o, part_ml, counters, q_pad, n_heads, n_kv_heads, n_splits,
       1.0f / sqrtf((float)head_dim), coop);
   LADE_LAUNCH_CHECK("attn_fwd_tc_kernel");
   return LADE_OK;

@@ -56,6 +56,35 @@ __device__ __forceinline__ bool row_sees(int rd_r, int r, int rd_c, int c, int l
   return c == r;  // PAD rows only see themselves
 }
 
+// 32 visibility bits of one query row for cache/step columns [col, col+32).
+//   rowmask row: bit c of word c/32 = row sees step column c (c < q_len), built by lade_step_layout from
+//   row_sees(); cache columns (col < kv_len) are visible to every row, columns >= kv_len + q_len to none.
+//   Prefill steps carry no rowmask: plain causal (modeling_llama.py:124-130).
+__device__ __forceinline__ uint32_t visible_bits32(const uint32_t* __restrict__ mrow, int mask_words, int col, int kv_len,
+                                                   int q_len, int is_prefill, int row) {
+  const int cs = col - kv_len;                       // first step column of the chunk (may be negative)
+  if (cs + 32 <= 0) return 0xffffffffu;
+  uint32_t step_bits;                                // visibility of step columns max(cs,0) .. cs+31, bit i <-> cs+i
+  if (is_prefill) {
+    const int n = (row < q_len ? row : -1) - cs + 1; // columns c <= row are visible
+    step_bits = n <= 0 ? 0u : (n >= 32 ? 0xffffffffu : ((1u << n) - 1u));
+    if (row >= q_len) step_bits = 0u;
+    const int nq = q_len - cs;                       // clip at q_len
+    if (nq < 32) step_bits &= nq <= 0 ? 0u : ((1u << nq) - 1u);
+    if (cs < 0) step_bits |= (1u << (-cs)) - 1u;
+    return step_bits;
+  }
+  if (!mrow) return cs < 0 ? ((1u << (-cs)) - 1u) : 0u;
+  if (cs < 0) {
+    const int k = -cs;
+    return ((1u << k) - 1u) | (mrow[0] << k);
+  }
+  const int w = cs >> 5, sh = cs & 31;
+  const uint32_t lo = w < mask_words ? mrow[w] : 0u;
+  const uint32_t hi = (w + 1) < mask_words ? mrow[w + 1] : 0u;
+  return __funnelshift_r(lo, hi, sh);
+}
+
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 }  // namespace lade

@@ -129,7 +129,7 @@ __global__ void reset_header_kernel(int* st, Dims d, int n_prompt, int n_window0
 
 // ---- step layout -------------------------------------------------------------------------------
 __global__ void step_layout_kernel(int* st, Dims d, int q_pad, int* ids_out, int* pos_out, int* rd_out,
-                                   int* lm_rows, int* meta) {
+                                   int* lm_rows, int* meta, unsigned* rowmask, int mask_words) {
   __shared__ int s_sizes[64];
   __shared__ int s_start[64];
   __shared__ int s_off[64];
@@ -236,6 +236,24 @@ __global__ void step_layout_kernel(int* st, Dims d, int q_pad, int* ids_out, int
       if (i < lg) row = q_len - lg + i;                                                 // modeling :1592
     }
     lm_rows[s] = row;
+  }
+  // Visibility bitmask of the step block, one row of `mask_words` words per query row: the attention
+  // kernels test these bits in registers instead of re-deriving the predicate per head and per layer.
+  if (rowmask != nullptr && phase != 0) {
+    __syncthreads();                                  // rd_out of every row is written
+    const int level_offset = s_hdr[6];
+    for (int w = t; w < q_pad * mask_words; w += blockDim.x) {
+      const int r = w / mask_words, wi = w % mask_words;
+      unsigned bits = 0;
+      if (r < q_len) {
+        const int rd_r = rd_out[r];
+        for (int i = 0; i < 32; ++i) {
+          const int c = wi * 32 + i;
+          if (c < q_len && row_sees(rd_r, r, rd_out[c], c, level_offset)) bits |= 1u << i;
+        }
+      }
+      rowmask[w] = bits;
+    }
   }
 }
 
@@ -693,11 +711,14 @@ int lade_ctx_reset(LadeCtx* ctx, void* stream, const int32_t* prompt_host, int32
 }
 
 int lade_step_layout(LadeCtx* ctx, void* stream, int32_t q_pad, int32_t* ids_out, int32_t* pos_out,
-                     int32_t* rowdesc_out, int32_t* lm_rows_out, int32_t* meta_out) {
+                     int32_t* rowdesc_out, int32_t* lm_rows_out, int32_t* meta_out, uint32_t* rowmask_out,
+                     int32_t mask_words) {
   if (!ctx || !ids_out || !pos_out || !rowdesc_out || !lm_rows_out || !meta_out || q_pad < 1) return LADE_EINVAL;
+  if (rowmask_out && mask_words * 32 < q_pad && mask_words > 0) return LADE_EINVAL;
   if (ctx->d.N - 1 > 64) return LADE_EUNSUPPORTED;
   step_layout_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(ctx->state, ctx->d, q_pad, ids_out, pos_out,
-                                                          rowdesc_out, lm_rows_out, meta_out);
+                                                          rowdesc_out, lm_rows_out, meta_out,
+                                                          mask_words > 0 ? rowmask_out : nullptr, mask_words);
   LADE_LAUNCH_CHECK("step_layout_kernel");
   return LADE_OK;
 }

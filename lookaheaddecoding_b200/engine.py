@@ -106,7 +106,7 @@ class LookaheadEngine:
         sm = torch.cuda.get_device_properties(self.dev).multi_processor_count
         q_tiles = (self.q_steady + 127) // 128
         # one CTA per SM (TMEM/smem bound): keep the split grid within a single wave
-        self.attn_splits = int(attn_splits) if attn_splits else max(1, sm // (self.nh * q_tiles))
+        self.attn_splits = int(attn_splits) if attn_splits else max(1, min(64, sm // (self.nh * q_tiles)))
 
         self._fuse_weights()
         self._rope_tables()
@@ -168,6 +168,8 @@ class LookaheadEngine:
         self.ids = torch.zeros(rows, **i32)
         self.pos = torch.zeros(rows, **i32)
         self.rowdesc = torch.zeros(rows, **i32)
+        self.mask_words = (max(self.q_steady, 32) + 31) // 32 + 1      # non-prefill steps are short
+        self.rowmask = torch.zeros(self.mask_words * 32 * self.mask_words, **i32)
         self.meta = torch.zeros(_cabi.META_INTS, **i32)
         self.lm_rows = torch.zeros(self.lm_cap, **i32)
         self.am = torch.zeros(self.lm_cap, **i32)
@@ -234,8 +236,10 @@ class LookaheadEngine:
         commit=False stops after the row-wise argmax (the sampling path decides on the host)."""
         lib, L = self.lib, self.L
         n = 0
+        mw = self.mask_words if rows <= self.mask_words * 32 else 0      # prefill-sized steps: causal, no rowmask
         check(lib.lade_step_layout(self._ctx, stream, rows, _ptr(self.ids), _ptr(self.pos), _ptr(self.rowdesc),
-                                   _ptr(self.lm_rows), _ptr(self.meta)), "lade_step_layout"); n += 1
+                                   _ptr(self.lm_rows), _ptr(self.meta), _ptr(self.rowmask) if mw else 0, mw),
+              "lade_step_layout"); n += 1
         h = self.h[:rows]
         torch.index_select(self.embed, 0, self.ids[:rows], out=h)
         xn, qkv, attn_out = self.xn[:rows], self.qkv[:rows], self.attn_out[:rows]
@@ -251,7 +255,7 @@ class LookaheadEngine:
             check(lib.lade_rope_append(stream, _ptr(qkv), _ptr(self.cos), _ptr(self.sin), _ptr(self.pos), _ptr(self.meta),
                                        _ptr(qb), _ptr(kc), _ptr(vc), rows, rows, self.nh, self.nkv, self.D,
                                        self.kv_capacity, self.table_len), "lade_rope_append"); n += 1
-            check(lib.lade_attn_fwd(stream, _ptr(qb), _ptr(kc), _ptr(vc), _ptr(attn_out), _ptr(self.rowdesc),
+            check(lib.lade_attn_fwd(stream, _ptr(qb), _ptr(kc), _ptr(vc), _ptr(attn_out), _ptr(self.rowmask) if mw else 0, mw,
                                     _ptr(self.meta), _ptr(self.attn_scratch), rows, self.nh, self.nkv, self.D,
                                     self.kv_capacity, kv_bound, self.attn_splits, self.attn_impl), "lade_attn_fwd"); n += 1
             torch.mm(attn_out, self.w_o[l].t(), out=o_buf)

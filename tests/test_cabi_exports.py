@@ -40,7 +40,7 @@ def test_host_only_entry_points():
     assert lib.lade_ctx_create(C.byref(bad), C.byref(out)) == -1          # LEVEL < 3
     bad.level, bad.guess_set_size = 3, -1
     assert lib.lade_ctx_create(C.byref(bad), C.byref(out)) == -4          # unbounded pool unsupported
-    assert lib.lade_attn_fwd(None, None, None, None, None, None, None, None, 1, 1, 1, 128, 1, 1, 1, 0) == -1
+    assert lib.lade_attn_fwd(None, None, None, None, None, None, 0, None, None, 1, 1, 1, 128, 1, 1, 1, 0) == -1
 
 
 def test_plugin_surface_signatures():

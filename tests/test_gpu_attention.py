@@ -19,8 +19,9 @@ ATOL_MAX, ATOL_MEAN = 2e-2, 2e-3
 IMPLS = [int(x) for x in os.environ.get("LADE_TEST_ATTN_IMPLS", "1").split(",")]
 
 
-def run_kernel(q, k, v, rowdesc, meta_vals, q_pad, n_splits, impl, kv_capacity=None):
-    """q [Hq, q_len, D], k/v [Hkv, T, D] (cache incl. step rows). Returns [q_len, Hq*D]."""
+def run_kernel(q, k, v, lay, meta_vals, q_pad, n_splits, impl, kv_capacity=None):
+    """q [Hq, q_len, D], k/v [Hkv, T, D] (cache incl. step rows). Returns [q_len, Hq*D].
+    The visibility bitmask handed to the kernel comes from the ORACLE's predicate (independent of the CUDA one)."""
     from lookaheaddecoding_b200 import _cabi
     lib = _cabi.load()
     Hq, q_len, D = q.shape
@@ -36,14 +37,17 @@ def run_kernel(q, k, v, rowdesc, meta_vals, q_pad, n_splits, impl, kv_capacity=N
     meta = torch.zeros(_cabi.META_INTS, dtype=torch.int32, device=dev)
     for key, val in meta_vals.items():
         meta[key] = val
-    rd_np = np.full(q_pad, 3 << 30, dtype=np.int64)
-    rd_np[:q_len] = np.asarray(rowdesc, dtype=np.int64)
-    rd = torch.from_numpy(rd_np.astype(np.uint32).view(np.int32)).to(dev)
+    mw = (q_pad + 31) // 32 + 1
+    bits = np.zeros((q_pad, mw * 32), dtype=bool)
+    if not lay.is_prefill:
+        bits[:q_len, :q_len] = LA.step_mask(lay)
+    words = np.packbits(bits.reshape(q_pad, mw, 32), axis=-1, bitorder="little").view(np.uint32).reshape(q_pad, mw)
+    rowmask = torch.from_numpy(words.view(np.int32).copy()).to(dev)
     nbytes = lib.lade_attn_scratch_bytes(q_pad, Hq, D, n_splits)
     scratch = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
     _cabi.check(lib.lade_attn_fwd(torch.cuda.current_stream().cuda_stream, qb.data_ptr(), kc.data_ptr(), vc.data_ptr(),
-                                  out.data_ptr(), rd.data_ptr(), meta.data_ptr(), scratch.data_ptr(), q_pad, Hq, Hkv, D,
-                                  cap, T, n_splits, impl), "lade_attn_fwd")
+                                  out.data_ptr(), 0 if lay.is_prefill else rowmask.data_ptr(), mw, meta.data_ptr(),
+                                  scratch.data_ptr(), q_pad, Hq, Hkv, D, cap, T, n_splits, impl), "lade_attn_fwd")
     torch.cuda.synchronize()
     assert int(scratch[:65536].view(torch.int32).abs().sum()) == 0, "split counters must self-reset"
     return out[:q_len]
@@ -82,7 +86,7 @@ def test_attention_vs_reference_module_output(name, impl):
     np.testing.assert_array_equal(LA.step_mask(lay), rows_to_bool(fx["mask_rows"])[:, kv_len:])
     q_pad = lay.q_len + 5
     for n_splits in (1, 3):
-        out = run_kernel(fx["q"].cuda(), fx["k"].cuda(), fx["v"].cuda(), layout_rowdesc(lay), meta_for(lay, kv_len, q_pad),
+        out = run_kernel(fx["q"].cuda(), fx["k"].cuda(), fx["v"].cuda(), lay, meta_for(lay, kv_len, q_pad),
                          q_pad, n_splits, impl)
         check_close(out.cpu(), fx["o"])
 
@@ -110,7 +114,7 @@ def test_attention_steady_shapes_vs_oracle(kv_len, W, N, g, Hq, Hkv, splits, imp
     k = torch.randn(Hkv, T, D, device="cuda").to(torch.bfloat16)
     v = torch.randn(Hkv, T, D, device="cuda").to(torch.bfloat16)
     q_pad = gs * (W + max(g, 1)) + 4
-    out = run_kernel(q, k, v, layout_rowdesc(lay), meta_for(lay, kv_len, q_pad), q_pad, splits, impl)
+    out = run_kernel(q, k, v, lay, meta_for(lay, kv_len, q_pad), q_pad, splits, impl)
     check_close(out, _oracle_attn(q, k, v, lay, kv_len))
 
 
@@ -123,7 +127,7 @@ def test_attention_prefill_causal_vs_oracle(P, Hq, Hkv, splits, impl):
     q = torch.randn(Hq, P, D, device="cuda").to(torch.bfloat16)
     k = torch.randn(Hkv, P, D, device="cuda").to(torch.bfloat16)
     v = torch.randn(Hkv, P, D, device="cuda").to(torch.bfloat16)
-    out = run_kernel(q, k, v, layout_rowdesc(lay), meta_for(lay, 0, P), P, splits, impl)
+    out = run_kernel(q, k, v, lay, meta_for(lay, 0, P), P, splits, impl)
     check_close(out, _oracle_attn(q, k, v, lay, 0))
 
 
@@ -142,5 +146,5 @@ def test_attention_lp_shapes_vs_oracle(impl):
         q = torch.randn(Hq, lay.q_len, 128, device="cuda").to(torch.bfloat16)
         k = torch.randn(Hq, T, 128, device="cuda").to(torch.bfloat16)
         v = torch.randn(Hq, T, 128, device="cuda").to(torch.bfloat16)
-        out = run_kernel(q, k, v, layout_rowdesc(lay), meta_for(lay, kv_len, lay.q_len), lay.q_len, 2, impl)
+        out = run_kernel(q, k, v, lay, meta_for(lay, kv_len, lay.q_len), lay.q_len, 2, impl)
         check_close(out, _oracle_attn(q, k, v, lay, kv_len))

@@ -88,8 +88,10 @@ def test_lp_device_state_machine_matches_reference(name):
             q_pad = bound
             ids, pos, rd = torch.zeros(q_cap, **i32), torch.zeros(q_cap, **i32), torch.zeros(q_cap, **i32)
             lm_rows = torch.zeros(lm_cap, **i32)
+            mw = (q_pad + 31) // 32 + 1
+            rowmask = torch.zeros(q_pad * mw, **i32)
             check(lib.lade_step_layout(ctxs[r], stream, q_pad, ids.data_ptr(), pos.data_ptr(), rd.data_ptr(),
-                                       lm_rows.data_ptr(), metas[r].data_ptr()), "layout")
+                                       lm_rows.data_ptr(), metas[r].data_ptr(), rowmask.data_ptr(), mw), "layout")
             m = metas[r].cpu().numpy()
             assert m[_cabi.M_Q_LEN] == q_len, f"rank {r} step {i}: q_len {m[_cabi.M_Q_LEN]} != {q_len}"
             assert ids[:q_len].cpu().tolist() == flat, f"rank {r} step {i} ids"
@@ -101,6 +103,10 @@ def test_lp_device_state_machine_matches_reference(name):
                 want = rows_to_bool(g["mask_rows"])[:, m[_cabi.M_KV_LEN]:]
                 got = _mask_from_rowdesc(rd[:q_len].cpu().numpy(), q_len, int(m[_cabi.M_LEVEL_OFFSET]))
                 np.testing.assert_array_equal(got, want, err_msg=f"rank {r} step {i} mask")
+                if i > 0:
+                    wd = rowmask.cpu().numpy().view(np.uint32).reshape(q_pad, mw)
+                    bits = np.unpackbits(wd.view(np.uint8).reshape(q_pad, mw * 4), axis=-1, bitorder="little").astype(bool)
+                    np.testing.assert_array_equal(bits[:q_len, :q_len], want, err_msg=f"rank {r} step {i} rowmask")
             am = np.zeros(lm_cap, dtype=np.int32)
             am[0] = g["first_guess"]
             am[1:1 + len(g["inp_tokens"])] = g["inp_tokens"]

@@ -87,8 +87,10 @@ def test_device_state_machine_matches_reference_trace(name):
         flat_pos = flat_pos + list(range(lst + 1, lst + 1 + GS)) * (len(gt) // GS)
         q_len = len(flat)
         q_pad = q_len + 3          # also exercise PAD rows
+        mw = (q_pad + 31) // 32 + 1
+        rowmask = torch.zeros(q_pad * mw, **i32)
         check(lib.lade_step_layout(ctx, stream, q_pad, ids.data_ptr(), pos.data_ptr(), rd.data_ptr(),
-                                   lm_rows.data_ptr(), meta.data_ptr()), "layout")
+                                   lm_rows.data_ptr(), meta.data_ptr(), rowmask.data_ptr(), mw), "layout")
         m = meta.cpu().numpy()
         assert m[_cabi.M_Q_LEN] == q_len, f"step {i}"
         assert m[_cabi.M_KV_LEN] + n_in == g["kvcache_len"] and m[_cabi.M_KV_LEN] + q_len == g["step_len"]
@@ -100,6 +102,11 @@ def test_device_state_machine_matches_reference_trace(name):
             want = rows_to_bool(g["mask_rows"])[:, m[_cabi.M_KV_LEN]:]
             got = _mask_from_rowdesc(rd_h, q_len, int(m[_cabi.M_LEVEL_OFFSET]))
             np.testing.assert_array_equal(got, want, err_msg=f"step {i} mask")
+            if i > 0:   # the bitmask the attention kernels consume (prefill steps carry none: plain causal)
+                wd = rowmask.cpu().numpy().view(np.uint32).reshape(q_pad, mw)
+                bits = np.unpackbits(wd.view(np.uint8).reshape(q_pad, mw * 4), axis=-1, bitorder="little").astype(bool)
+                np.testing.assert_array_equal(bits[:q_len, :q_len], want, err_msg=f"step {i} rowmask")
+                assert not bits[q_len:].any() and not bits[:, q_len:].any()
         tiny = int(m[_cabi.M_TINY])
         lmr = lm_rows.cpu().numpy()
         assert lmr[0] == n_in - 1
