@@ -188,18 +188,31 @@ def attn_roofline(eng, shape, reps=5):
     stream = torch.cuda.current_stream(eng.dev)
 
     def one_pass():
+        cs = torch.cuda.current_stream(eng.dev).cuda_stream
         for l in range(eng.L):
-            _cabi.check(lib.lade_attn_fwd(stream.cuda_stream, qb.data_ptr(), eng.kv[l, 0].data_ptr(), eng.kv[l, 1].data_ptr(),
+            _cabi.check(lib.lade_attn_fwd(cs, qb.data_ptr(), eng.kv[l, 0].data_ptr(), eng.kv[l, 1].data_ptr(),
                                           eng.attn_out.data_ptr(), rowmask.data_ptr(), mw, meta.data_ptr(),
                                           eng.attn_scratch.data_ptr(), rows, eng.nh, eng.nkv, eng.D, eng.kv_capacity,
                                           eng.kv_capacity, eng.attn_splits, eng.attn_impl))
     for _ in range(3):
         one_pass()
     torch.cuda.synchronize()
+    # one pass over the L layer caches captured in a CUDA graph (the launch rate of a python loop, ~20 us per
+    # ctypes call, must not bound the kernel measurement); events on the replaying stream
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream(device=eng.dev)
+    side.wait_stream(torch.cuda.current_stream(eng.dev))
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            one_pass()
+    torch.cuda.current_stream(eng.dev).wait_stream(side)
+    g.replay()
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream(eng.dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(reps):
-        one_pass()
+        g.replay()
     e1.record(stream)
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / (reps * eng.L)

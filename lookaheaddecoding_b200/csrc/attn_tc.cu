@@ -195,7 +195,20 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int b = 0; b < 2; ++b) { mbar_init(BAR(B_SFULL + b), 1); mbar_init(BAR(B_PFULL + b), 256); }
     mbar_init(BAR(B_OFINAL), 1);
     fence_barrier_init();
-    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    // start the memory stream before anything else: Q and the first STAGES K/V tiles are in flight while the
+    // other warps allocate TMEM and meet at the barrier below
+    mbar_expect_tx(BAR(B_QFULL), TC_TILE_BYTES);
+    tma_load_3d(sQ_a, &tmQ, BAR(B_QFULL), 0, mt * TC_BM, h);
+    tma_load_3d(sQ_a + TC_HALF_BYTES, &tmQ, BAR(B_QFULL), 64, mt * TC_BM, h);
+    for (int j = 0; j < my_tiles && j < TC_STAGES; ++j) {
+      const int row0 = (tile_lo + j) * TC_BN;
+      mbar_expect_tx(BAR(B_KFULL + j), TC_TILE_BYTES);
+      tma_load_3d(sK_a(j), &tmK, BAR(B_KFULL + j), 0, row0, hk);
+      tma_load_3d(sK_a(j) + TC_HALF_BYTES, &tmK, BAR(B_KFULL + j), 64, row0, hk);
+      mbar_expect_tx(BAR(B_VFULL + j), TC_TILE_BYTES);
+      tma_load_3d(sV_a(j), &tmV, BAR(B_VFULL + j), 0, row0, hk);
+      tma_load_3d(sV_a(j) + TC_HALF_BYTES, &tmV, BAR(B_VFULL + j), 64, row0, hk);
+    }
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
@@ -205,14 +218,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tmem_O = tmem_base + 256;
 
   if (warp == 0) {
-    // ================= TMA producer =================
+    // ================= TMA producer (tiles beyond the first STAGES; the rest was issued in the prologue) =====
     if (lane == 0) {
-      mbar_expect_tx(BAR(B_QFULL), TC_TILE_BYTES);
-      tma_load_3d(sQ_a, &tmQ, BAR(B_QFULL), 0, mt * TC_BM, h);
-      tma_load_3d(sQ_a + TC_HALF_BYTES, &tmQ, BAR(B_QFULL), 64, mt * TC_BM, h);
-      for (int j = 0; j < my_tiles; ++j) {
+      for (int j = TC_STAGES; j < my_tiles; ++j) {
         const int s = j % TC_STAGES;
-        if (j >= TC_STAGES) mbar_wait(BAR(B_FREE + s), ((j / TC_STAGES) - 1) & 1);
+        mbar_wait(BAR(B_FREE + s), ((j / TC_STAGES) - 1) & 1);
         const int row0 = (tile_lo + j) * TC_BN;
         mbar_expect_tx(BAR(B_KFULL + s), TC_TILE_BYTES);
         tma_load_3d(sK_a(s), &tmK, BAR(B_KFULL + s), 0, row0, hk);
@@ -293,8 +303,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_ld32(ts + c * 32, v);
         tmem_ld_wait();
         const uint32_t mb = c == 0 ? mb0 : mb1;
+        if (mb == 0xffffffffu) {                     // pure-cache chunk: no per-element mask work
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx_raw = fmaxf(mx_raw, ((mb >> i) & 1u) ? v[i] : -INFINITY);
+          for (int i = 0; i < 32; ++i) mx_raw = fmaxf(mx_raw, v[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx_raw = fmaxf(mx_raw, ((mb >> i) & 1u) ? v[i] : -INFINITY);
+        }
       }
       float* xch = s_xch + (j & 1) * 256;            // slot parity: no write-after-read race across tiles
       xch[half * 128 + row_l] = mx_raw;
@@ -336,15 +351,23 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_ld32(ts + c * 32, v);
         tmem_ld_wait();
         const uint32_t mb = c == 0 ? mb0 : mb1;
+        const bool all_vis = (mb == 0xffffffffu);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float p[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
+          for (int e = 0; e < 8; e += 2) {
             const int i = g * 8 + e;
-            const float x = bf16_round(bf16_round(v[i]) * inv_sqrt_d);        // reference rounding points
-            p[e] = ((mb >> i) & 1u) ? ex2_approx(x * TC_LOG2E - off) : 0.f;
-            psum += p[e];
+            // reference rounding points, two elements per cvt: bf16(bf16(s) * (1/sqrt(d)))
+            float2 r1 = __bfloat1622float2(__floats2bfloat162_rn(v[i], v[i + 1]));
+            float2 r2 = __bfloat1622float2(__floats2bfloat162_rn(r1.x * inv_sqrt_d, r1.y * inv_sqrt_d));
+            p[e] = ex2_approx(r2.x * TC_LOG2E - off);
+            p[e + 1] = ex2_approx(r2.y * TC_LOG2E - off);
+            if (!all_vis) {
+              if (!((mb >> i) & 1u)) p[e] = 0.f;
+              if (!((mb >> (i + 1)) & 1u)) p[e + 1] = 0.f;
+            }
+            psum += p[e] + p[e + 1];
           }
           uint4 pk;
           pk.x = pack2_bf16(p[0], p[1]); pk.y = pack2_bf16(p[2], p[3]);

@@ -70,9 +70,8 @@ def main():
             for ns in a.splits:
                 nb = lib.lade_attn_scratch_bytes(q_len, H, D, ns)
                 scratch = torch.zeros(nb, dtype=torch.uint8, device=dev)
-                st = torch.cuda.current_stream()
-
                 def one_pass():
+                    st = torch.cuda.current_stream()
                     for l in range(L):
                         _cabi.check(lib.lade_attn_fwd(st.cuda_stream, q.data_ptr(), kvc[l, 0].data_ptr(), kvc[l, 1].data_ptr(),
                                                       out.data_ptr(), rd.data_ptr(), mw, meta.data_ptr(), scratch.data_ptr(), q_len,
@@ -80,10 +79,22 @@ def main():
                 for _ in range(2):
                     one_pass()
                 torch.cuda.synchronize()
+                # capture one pass over the L caches in a CUDA graph: python/ctypes launch overhead (~20 us per
+                # call) would otherwise bound the measurement
+                g = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    with torch.cuda.graph(g, stream=side):
+                        st = torch.cuda.current_stream()
+                        one_pass()
+                torch.cuda.current_stream().wait_stream(side)
+                g.replay()
+                torch.cuda.synchronize()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 for _ in range(a.reps):
-                    one_pass()
+                    g.replay()
                 e1.record()
                 torch.cuda.synchronize()
                 us = e0.elapsed_time(e1) * 1e3 / (a.reps * L)
