@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--attn-splits", type=int, default=0)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-cuda", action="store_true",
+                    help="skip timing the unmodified reference's CUDA-eager loop (needs baseline/_ref)")
     ap.add_argument("--cuda-profiler-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed region (use with ncu --profile-from-start off)")
     return ap.parse_args()
@@ -258,6 +260,67 @@ def cpu_baseline(shape, W, N, G, n_threads, budget_layers=(1, 2), prompt_len=64,
                       f"({times[l1]:.2f}s@{l1}L, {times[l2]:.2f}s@{l2}L -> {t_full:.2f}s/step), {toks / steps:.2f} tokens/step"}
 
 
+def reference_cuda_eager(shape, W, N, G, P, max_new, device):
+    """The UNMODIFIED reference (pip-installed into the git-ignored baseline/_ref, loaded through the App.-C shims of
+    oracle/ref_shim.py) running its own eager lookahead loop on the same GPU: the denominator of BASELINE.json's
+    ">= 1.8x over the reference's own CUDA eager lookahead".  Extra reporting only; skipped when baseline/_ref is absent."""
+    import torch
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isfile(os.path.join(ref_root, "lade", "decoding.py")):
+        return {"unavailable": "baseline/_ref not present"}
+    os.environ["LADE_REFERENCE_ROOT"] = ref_root
+    import importlib
+    from oracle import ref_shim as R
+    importlib.reload(R)
+    from transformers import GenerationConfig, MaxLengthCriteria, StoppingCriteriaList
+    decoding, modeling = R.load_reference()
+    cfg = R.make_llama_config(hidden=shape["hidden"], layers=shape["layers"], heads=shape["heads"], kv_heads=shape["kv_heads"],
+                              inter=shape["inter"], vocab=shape["vocab"], max_pos=shape["max_pos"],
+                              rope_theta=shape["rope_theta"], eps=shape["eps"])
+    old_dtype = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    torch.set_default_device(device)          # also makes the mask builder's torch.tensor([...]) land on the GPU
+    try:
+        torch.manual_seed(0)
+        model = modeling.LlamaForCausalLM(cfg).eval()
+        with torch.no_grad():
+            for p_ in model.parameters():
+                if p_.dim() >= 2:
+                    p_.normal_(0.0, 0.02)
+        model.generation_config = GenerationConfig(pad_token_id=0, eos_token_id=None)
+        torch.manual_seed(1)
+        prompt = torch.randint(3, shape["vocab"], (1, P), device=device)
+
+        def run(n_new):
+            decoding.CONFIG_MAP.clear()
+            decoding.CONFIG_MAP.update(dict(WINDOW_SIZE=W, LEVEL=N, GUESS_SET_SIZE=G, DEBUG=1, log=[]))
+            random.seed(0)
+            with torch.no_grad():
+                out = decoding.jacobi_greedy_search_multilevel(
+                    model, prompt, stopping_criteria=StoppingCriteriaList([MaxLengthCriteria(P + n_new)]),
+                    attention_mask=torch.ones_like(prompt), use_cache=True, return_dict_in_generate=False,
+                    output_attentions=False, output_hidden_states=False, output_scores=False, pad_token_id=0,
+                    eos_token_id=None)
+            return out.shape[1] - P, decoding.CONFIG_MAP["log"][-1][1]
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            run(4)                                  # warm-up (minimal.py:30)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            toks, steps = run(max_new)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        del model
+        torch.cuda.empty_cache()
+        return {"value": round(toks / dt, 2), "unit": "tokens/s", "tokens": toks, "decode_steps": steps,
+                "ms_per_decode_step": round(1e3 * dt / steps, 3), "accepted_tokens_per_step": round(toks / steps, 3),
+                "source": "unmodified reference (baseline/_ref, shims of SURVEY App. C), eager attention, same GPU, same "
+                          "shape/prompt length/seeds; wall clock around one generate after a warm-up (minimal.py:34-45)"}
+    finally:
+        torch.set_default_dtype(old_dtype)
+        torch.set_default_device("cpu")
+
+
 def main():
     args = parse()
     shape, W, N, G, P = WORKLOADS[args.workload]
@@ -370,6 +433,12 @@ def main():
     if rank != 0:
         return
     roof = attn_roofline(eng, shape)
+    ref_cuda = None
+    if not args.no_reference_cuda and world == 1:
+        try:
+            ref_cuda = reference_cuda_eager(shape, W, N, G, P, args.max_new, dev)
+        except Exception as ex:   # reporting only
+            ref_cuda = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
     clocks = sampler.summary()
     cb = None
     if not args.no_cpu_baseline:
@@ -387,7 +456,8 @@ def main():
         "ms_per_decode_step": round(dev_ms / steps, 4),
         "e2e": {"value": round(e2e_toks / e2e_s, 2), "unit": "tokens/s", "h2d_bytes_per_step": P * 8,
                 "d2h_bytes_per_step": (P + args.max_new) * 8 + int(steps / args.steps) * 48 * 4},
-        "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cb, "clocks": clocks,
+        "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cb, "reference_cuda_eager": ref_cuda,
+        "clocks": clocks,
         "attn_impl": eng.attn_impl, "attn_splits": eng.attn_splits, "cuda_graph": eng.use_cuda_graph,
     }
     print(json.dumps(line))

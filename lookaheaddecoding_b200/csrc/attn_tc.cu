@@ -478,41 +478,75 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   const int HD = n_heads * TC_D;
   const long long rows_pad = (long long)q_tiles * TC_BM;
-  // phase A: per-row merge weights w_s = 2^(m_s - m) / sum_s l_s 2^(m_s - m)  -> smem (Q tile is dead)
-  float* s_w = reinterpret_cast<float*>(smem);
-  for (int rl = row_lo + threadIdx.x; rl < row_hi; rl += TC_THREADS) {
-    const int row = mt * TC_BM + rl;
+  // phase A: per-row merge weights w_s = 2^(m_s - m) / sum_s l_s 2^(m_s - m)  -> smem (the Q tile is dead).
+  // Every load of the merge is independent of the others: one (row, split) pair per thread here, unrolled
+  // batches below, so the L2 latency is paid once, not once per split.
+  const int n_rows = row_hi - row_lo;
+  float* s_w = reinterpret_cast<float*>(smem);                 // [n_rows][n_active] weights
+  float2* s_ml = reinterpret_cast<float2*>(smem + TC_TILE_BYTES);   // [n_rows][n_active] (m, l), dead K/V stage 0
+  for (int i = threadIdx.x; i < n_rows * n_active; i += TC_THREADS) {
+    const int rl = row_lo + i / n_active, sp = i % n_active;
+    s_ml[i] = __ldcg(reinterpret_cast<const float2*>(part_ml + ((((long long)sp * n_heads + h) * rows_pad) + mt * TC_BM + rl) * 2));
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < n_rows; r += TC_THREADS) {
     float mmax = -INFINITY;
-    for (int s = 0; s < n_active; ++s)
-      mmax = fmaxf(mmax, __ldcg(part_ml + ((((long long)s * n_heads + h) * rows_pad) + row) * 2));
+    for (int sp = 0; sp < n_active; ++sp) mmax = fmaxf(mmax, s_ml[r * n_active + sp].x);
     float lsum = 0.f;
-    for (int s = 0; s < n_active; ++s) {
-      const float2 ml = __ldcg(reinterpret_cast<const float2*>(part_ml + ((((long long)s * n_heads + h) * rows_pad) + row) * 2));
+    for (int sp = 0; sp < n_active; ++sp) {
+      const float2 ml = s_ml[r * n_active + sp];
       const float wgt = (ml.x == -INFINITY) ? 0.f : exp2f((ml.x - mmax) * TC_LOG2E);
-      s_w[rl * n_active + s] = wgt;
+      s_w[r * n_active + sp] = wgt;
       lsum += ml.y * wgt;
     }
     const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
-    for (int s = 0; s < n_active; ++s) s_w[rl * n_active + s] *= inv;
+    for (int sp = 0; sp < n_active; ++sp) s_w[r * n_active + sp] *= inv;
   }
   __syncthreads();
-  // phase B: out[row] = sum_s w_s O_s[row]; all loads of an item are independent
-  const int n_items = (row_hi - row_lo) * (TC_D / 4);
-  for (int idx = threadIdx.x; idx < n_items; idx += TC_THREADS) {
-    const int rl = row_lo + idx / (TC_D / 4), c4 = idx % (TC_D / 4);
-    const int row = mt * TC_BM + rl;
-    if (row >= q_pad) continue;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int s = 0; s < n_active; ++s) {
-      const float4 v = __ldcg(reinterpret_cast<const float4*>(part_o + ((((long long)s * n_heads + h) * rows_pad) + row) * TC_D + c4 * 4));
-      const float wgt = s_w[rl * n_active + s];
-      acc.x += v.x * wgt; acc.y += v.y * wgt; acc.z += v.z * wgt; acc.w += v.w * wgt;
+  // phase B: out[row] = sum_s w_s O_s[row], four items per thread per round, up to 8 splits per batch in flight
+  const int n_items = n_rows * (TC_D / 4);
+  const float* po_h = part_o + ((long long)h * rows_pad + mt * TC_BM) * TC_D;
+  const long long split_stride = (long long)n_heads * rows_pad * TC_D;
+  for (int base = 0; base < n_items; base += TC_THREADS * 4) {
+    float4 acc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s0 = 0; s0 < n_active; s0 += 8) {
+      float4 v[4][8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int idx = base + k * TC_THREADS + threadIdx.x;
+        const int rl = row_lo + idx / (TC_D / 4), c4 = idx % (TC_D / 4);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const bool ok = idx < n_items && (s0 + u) < n_active;
+          v[k][u] = ok ? __ldcg(reinterpret_cast<const float4*>(po_h + (long long)(s0 + u) * split_stride + (long long)rl * TC_D + c4 * 4))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int idx = base + k * TC_THREADS + threadIdx.x;
+        const int r = idx / (TC_D / 4);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float wgt = (idx < n_items && (s0 + u) < n_active) ? s_w[r * n_active + s0 + u] : 0.f;
+          acc[k].x += v[k][u].x * wgt; acc[k].y += v[k][u].y * wgt; acc[k].z += v[k][u].z * wgt; acc[k].w += v[k][u].w * wgt;
+        }
+      }
     }
-    uint2 pk;
-    pk.x = pack2_bf16(acc.x, acc.y);
-    pk.y = pack2_bf16(acc.z, acc.w);
-    *reinterpret_cast<uint2*>(out + (long long)row * HD + h * TC_D + c4 * 4) = pk;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int idx = base + k * TC_THREADS + threadIdx.x;
+      if (idx >= n_items) continue;
+      const int rl = row_lo + idx / (TC_D / 4), c4 = idx % (TC_D / 4);
+      const int row = mt * TC_BM + rl;
+      if (row >= q_pad) continue;
+      uint2 pk;
+      pk.x = pack2_bf16(acc[k].x, acc[k].y);
+      pk.y = pack2_bf16(acc[k].z, acc[k].w);
+      *reinterpret_cast<uint2*>(out + (long long)row * HD + h * TC_D + c4 * 4) = pk;
+    }
   }
   // counters return to zero once every participant is through
   if (coop) {

@@ -10,8 +10,12 @@ It exists for exactly two purposes:
     produce the committed golden fixtures that pin ``oracle/``;
   * CPU tests that are skipped when ``/root/reference`` is absent (e.g. on the GPU box).
 
+  * ``bench.py``'s optional ``reference_cuda_eager`` leg points ``LADE_REFERENCE_ROOT`` at ``baseline/_ref``
+    (the reference pip-installed there, git-ignored, never part of the repo history) to time the reference's
+    own CUDA-eager loop on the GPU box.
+
 Nothing in the product package may import this file.  ``/root/reference`` does not exist on the
-GPU box, so nothing here is used by ``-m gpu`` tests, ``smoke()`` or ``bench.py``.
+GPU box, so nothing here reads it in ``-m gpu`` tests, ``smoke()`` or ``bench.py``.
 """
 from __future__ import annotations
 
@@ -55,12 +59,13 @@ def load_reference():
     # touches GenerationMixin.greedy_search, gone in transformers 5.x).
     import importlib.util
 
-    pkg = types.ModuleType("lade")
+    # private package names: this repo ships its own `lade` alias package, which must not be shadowed
+    pkg = types.ModuleType("lade_reference")
     pkg.__path__ = [os.path.join(REFERENCE_ROOT, "lade")]
-    sys.modules.setdefault("lade", pkg)
-    models_pkg = types.ModuleType("lade.models")
+    sys.modules.setdefault("lade_reference", pkg)
+    models_pkg = types.ModuleType("lade_reference.models")
     models_pkg.__path__ = [os.path.join(REFERENCE_ROOT, "lade", "models")]
-    sys.modules.setdefault("lade.models", models_pkg)
+    sys.modules.setdefault("lade_reference.models", models_pkg)
 
     def _load(modname, relpath):
         if modname in sys.modules:
@@ -71,8 +76,8 @@ def load_reference():
         spec.loader.exec_module(mod)
         return mod
 
-    decoding = _load("lade.decoding", "lade/decoding.py")
-    modeling = _load("lade.models.modeling_llama", "lade/models/modeling_llama.py")
+    decoding = _load("lade_reference.decoding", "lade/decoding.py")
+    modeling = _load("lade_reference.models.modeling_llama", "lade/models/modeling_llama.py")
 
     # shim 5: the loop calls self._update_model_kwargs_for_generation (HF mixin)
     from transformers import GenerationMixin
