@@ -162,6 +162,10 @@ int lade_attn_fwd(void* stream, const void* q, const void* k_cache, const void* 
                   int32_t kv_bound /* host upper bound of kv_len + q_len */, int32_t n_splits,
                   int32_t impl /* 0 = default (= 2), 1 = mma.sync path, 2 = tcgen05/TMA path */);
 int64_t lade_attn_scratch_bytes(int32_t q_pad, int32_t n_heads, int32_t head_dim, int32_t n_splits);
+/* Profiling aid: when set (device buffer of 8 int64 per CTA, or NULL to disable) the tcgen05 kernel records
+ * clock64() at its phase boundaries (start, first K tile landed, first S ready, O final, partials written,
+ * siblings arrived, merged, end). */
+int lade_debug_attn_timing(void* dev_buffer);
 
 /* act = bf16(silu(gate)) * up on the fused [rows][2*inter] projection.  LlamaMLP, modeling_llama.py:378. */
 int lade_swiglu(void* stream, const void* gate_up, void* out, int32_t rows, int32_t inter);

@@ -25,11 +25,11 @@ constexpr int TC_BM = 128;
 constexpr int TC_BN = 128;
 constexpr int TC_D = 128;
 constexpr int TC_STAGES = 3;
-constexpr int TC_THREADS = 320;
+constexpr int TC_SOFTMAX_THREADS = 512;            // 16 warps: 4 threads per query row
+constexpr int TC_THREADS = 64 + TC_SOFTMAX_THREADS;
 constexpr int TC_TILE_BYTES = 128 * 128 * 2;   // one [128 x 128] bf16 tile = two [128 x 64] swizzle blocks
 constexpr int TC_HALF_BYTES = TC_TILE_BYTES / 2;
-constexpr int TC_XCH_FLOATS = 512;   // row-max / row-sum exchange between the two column halves
-constexpr int TC_MAX_COUNTERS = 16384;
+constexpr int TC_XCH_FLOATS = 512;   // 2 KB: row maxima (bf16 [2][4][128]) / row sums (fp32 [4][128]) of the 4 threads of a row
 constexpr int TC_SMEM_TILES = TC_TILE_BYTES * (1 + 2 * TC_STAGES);
 constexpr int TC_SMEM_BYTES = TC_SMEM_TILES + 256 + TC_XCH_FLOATS * 4;
 constexpr float TC_LOG2E = 1.4426950408889634f;
@@ -147,17 +147,44 @@ __device__ __forceinline__ unsigned pack2_bf16(float lo, float hi) {
   return *reinterpret_cast<unsigned*>(&v);
 }
 
+// Optional per-CTA phase timestamps (clock64) for profiling the kernel's own timeline: 8 slots per CTA.
+__device__ long long* g_attn_timing = nullptr;
+#define TC_STAMP(slot, tid) do { if (tbuf && threadIdx.x == (tid)) tbuf[slot] = clock64(); } while (0)
+enum { TS_START = 0, TS_KFULL0 = 1, TS_SFULL0 = 2, TS_OFINAL = 3, TS_STAGED = 4, TS_CLUSTER = 5, TS_MERGED = 6, TS_END = 7 };
+
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 ld_dsmem_f2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+
+constexpr int TC_SO_STRIDE = 132;                       // floats per staged O row (528 B: conflict-free float4 rows)
+constexpr int TC_SO_OFFSET = TC_TILE_BYTES;             // staged O lives in the (dead) K/V stages
+constexpr int TC_SML_OFFSET = 0;                        // (m, l) per row: 1 KB in the (dead) Q tile
+constexpr int TC_SW_OFFSET = 4096;                      // merge weights [rows][cluster] <= 4 KB
+
 // ---- kernel ---------------------------------------------------------------------------------------------
+// grid (n_splits, heads, q tiles); when n_splits > 1 the n_splits CTAs of one (head, q tile) form a thread-block
+// cluster and merge their split-KV partials through distributed shared memory.
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out,
-                   const uint32_t* __restrict__ rowmask, int mask_words, const int* __restrict__ meta,
-                   float* __restrict__ part_o,
-                   float* __restrict__ part_ml, int* __restrict__ counters, int q_pad, int n_heads, int n_kv_heads,
-                   int n_splits, float inv_sqrt_d, int coop) {
+                   const uint32_t* __restrict__ rowmask, int mask_words, const int* __restrict__ meta, int q_pad,
+                   int n_heads, int n_kv_heads, int n_splits, float inv_sqrt_d) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int split = blockIdx.x, h = blockIdx.y, mt = blockIdx.z;
-  const int q_tiles = gridDim.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const int q_len = meta[LADE_M_Q_LEN];
@@ -169,10 +196,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int n_tiles = (Tm + TC_BN - 1) / TC_BN;
   const int tps = (n_tiles + n_splits - 1) / n_splits;
   const int n_active = (n_tiles + tps - 1) / tps;
-  if (split >= n_active) return;
+  const bool active = split < n_active;
   const int tile_lo = split * tps;
-  const int my_tiles = min(n_tiles, tile_lo + tps) - tile_lo;
+  const int my_tiles = active ? min(n_tiles, tile_lo + tps) - tile_lo : 0;
   const int hk = h / (n_heads / n_kv_heads);
+  const int HD = n_heads * TC_D;
+  long long* tbuf = g_attn_timing ? g_attn_timing + 8ll * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
+  TC_STAMP(TS_START, 0);
 
   unsigned char* sQ = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_SMEM_TILES);
@@ -182,42 +212,46 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int B_QFULL = 0, B_KFULL = 1, B_VFULL = 1 + TC_STAGES, B_FREE = 1 + 2 * TC_STAGES,
             B_SFULL = 1 + 3 * TC_STAGES, B_PFULL = 3 + 3 * TC_STAGES, B_OFINAL = 5 + 3 * TC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
-  int* s_flag = reinterpret_cast<int*>(bars + 25);
-  float* s_xch = reinterpret_cast<float*>(smem + TC_SMEM_TILES + 256);
+  __nv_bfloat16* s_xmax = reinterpret_cast<__nv_bfloat16*>(smem + TC_SMEM_TILES + 256);   // [2][4][128] row maxima
+  float* s_xsum = reinterpret_cast<float*>(smem + TC_SMEM_TILES + 256);                   // [4][128] row sums (epilogue)
   const uint32_t sQ_a = smem_u32(sQ);
   auto sK_a = [&](int s) { return sQ_a + (uint32_t)TC_TILE_BYTES * (1 + 2 * s); };
   auto sV_a = [&](int s) { return sQ_a + (uint32_t)TC_TILE_BYTES * (2 + 2 * s); };
 
-  if (threadIdx.x == 0) {
-    if ((sQ_a & 1023u) != 0) __trap();   // SWIZZLE_128B tiles need 1024-byte alignment
-    mbar_init(BAR(B_QFULL), 1);
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(BAR(B_KFULL + s), 1); mbar_init(BAR(B_VFULL + s), 1); mbar_init(BAR(B_FREE + s), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(BAR(B_SFULL + b), 1); mbar_init(BAR(B_PFULL + b), 256); }
-    mbar_init(BAR(B_OFINAL), 1);
-    fence_barrier_init();
-    // start the memory stream before anything else: Q and the first STAGES K/V tiles are in flight while the
-    // other warps allocate TMEM and meet at the barrier below
-    mbar_expect_tx(BAR(B_QFULL), TC_TILE_BYTES);
-    tma_load_3d(sQ_a, &tmQ, BAR(B_QFULL), 0, mt * TC_BM, h);
-    tma_load_3d(sQ_a + TC_HALF_BYTES, &tmQ, BAR(B_QFULL), 64, mt * TC_BM, h);
-    for (int j = 0; j < my_tiles && j < TC_STAGES; ++j) {
-      const int row0 = (tile_lo + j) * TC_BN;
-      mbar_expect_tx(BAR(B_KFULL + j), TC_TILE_BYTES);
-      tma_load_3d(sK_a(j), &tmK, BAR(B_KFULL + j), 0, row0, hk);
-      tma_load_3d(sK_a(j) + TC_HALF_BYTES, &tmK, BAR(B_KFULL + j), 64, row0, hk);
-      mbar_expect_tx(BAR(B_VFULL + j), TC_TILE_BYTES);
-      tma_load_3d(sV_a(j), &tmV, BAR(B_VFULL + j), 0, row0, hk);
-      tma_load_3d(sV_a(j) + TC_HALF_BYTES, &tmV, BAR(B_VFULL + j), 64, row0, hk);
+  if (active) {
+    if (threadIdx.x == 0) {
+      if ((sQ_a & 1023u) != 0) __trap();   // SWIZZLE_128B tiles need 1024-byte alignment
+      mbar_init(BAR(B_QFULL), 1);
+      for (int s = 0; s < TC_STAGES; ++s) { mbar_init(BAR(B_KFULL + s), 1); mbar_init(BAR(B_VFULL + s), 1); mbar_init(BAR(B_FREE + s), 1); }
+      for (int b = 0; b < 2; ++b) { mbar_init(BAR(B_SFULL + b), 1); mbar_init(BAR(B_PFULL + b), TC_SOFTMAX_THREADS); }
+      mbar_init(BAR(B_OFINAL), 1);
+      fence_barrier_init();
+      // start the memory stream before anything else: Q and the first STAGES K/V tiles are in flight while the
+      // other warps allocate TMEM and meet at the barrier below
+      mbar_expect_tx(BAR(B_QFULL), TC_TILE_BYTES);
+      tma_load_3d(sQ_a, &tmQ, BAR(B_QFULL), 0, mt * TC_BM, h);
+      tma_load_3d(sQ_a + TC_HALF_BYTES, &tmQ, BAR(B_QFULL), 64, mt * TC_BM, h);
+      for (int j = 0; j < my_tiles && j < TC_STAGES; ++j) {
+        const int row0 = (tile_lo + j) * TC_BN;
+        mbar_expect_tx(BAR(B_KFULL + j), TC_TILE_BYTES);
+        tma_load_3d(sK_a(j), &tmK, BAR(B_KFULL + j), 0, row0, hk);
+        tma_load_3d(sK_a(j) + TC_HALF_BYTES, &tmK, BAR(B_KFULL + j), 64, row0, hk);
+        mbar_expect_tx(BAR(B_VFULL + j), TC_TILE_BYTES);
+        tma_load_3d(sV_a(j), &tmV, BAR(B_VFULL + j), 0, row0, hk);
+        tma_load_3d(sV_a(j) + TC_HALF_BYTES, &tmV, BAR(B_VFULL + j), 64, row0, hk);
+      }
     }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = active ? *tmem_slot : 0u;
   const uint32_t tmem_O = tmem_base + 256;
 
-  if (warp == 0) {
+  if (!active) {
+    // an idle split of the cluster: nothing to compute, but it must meet its siblings at the cluster barriers
+  } else if (warp == 0) {
     // ================= TMA producer (tiles beyond the first STAGES; the rest was issued in the prologue) =====
     if (lane == 0) {
       for (int j = TC_STAGES; j < my_tiles; ++j) {
@@ -253,6 +287,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         umma_commit(BAR(B_SFULL + (j & 1)));
       };
       mbar_wait(BAR(B_QFULL), 0);
+      mbar_wait(BAR(B_KFULL), 0);
+      if (tbuf) tbuf[TS_KFULL0] = clock64();
       issue_qk(0);
       for (int j = 0; j < my_tiles; ++j) {
         if (j + 1 < my_tiles) issue_qk(j + 1);
@@ -272,51 +308,44 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else {
-    // ================= softmax: two threads per query row =================
-    // Warp w (2..9): TMEM quadrant (w & 3) = rows, column half (w - 2) >> 2 = kv columns [64*half, 64*half+64)
-    // of every tile.  The halves meet once per tile (row max) through smem + a named barrier.  Code size
-    // matters (32 KB instruction cache): 32-column chunks, rolled loops, two passes over TMEM.
+    // ================= softmax: four threads per query row =================
+    // Warp w (2..17): TMEM quadrant (w & 3) = 32 rows, column quarter (w - 2) >> 2 = 32 of the tile's 128 kv
+    // columns.  The four threads of a row meet once per tile (row max, exchanged as bf16 -- the rounded max
+    // is exactly what the reference's rounding points produce) through smem + a named barrier.
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int q4 = (warp - 2) >> 2;
     const int row_l = quad * 32 + lane;             // TMEM lane == row inside the tile
     const int row = mt * TC_BM + row_l;             // step-local row
     const uint32_t* mrow = (row < q_pad && !is_prefill && rowmask != nullptr) ? rowmask + (long long)row * mask_words : nullptr;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const uint32_t tO = tmem_O + lane_addr + (uint32_t)q4 * 32u;
     float m_used = -INFINITY, l_sum = 0.f;
     for (int j = 0; j < my_tiles; ++j) {
       const int buf = j & 1, s = j % TC_STAGES;
       mbar_wait(BAR(B_SFULL + buf), (j >> 1) & 1);
       tc_fence_after();
-      const uint32_t ts = tmem_base + lane_addr + (uint32_t)buf * 128u + (uint32_t)half * 64u;
-      const int col0 = (tile_lo + j) * TC_BN + half * 64;
-      const bool need_mask = (col0 + 64 > kv_len);
-      uint32_t mb0 = 0xffffffffu, mb1 = 0xffffffffu;
-      if (need_mask) {
-        mb0 = visible_bits32(mrow, mask_words, col0, kv_len, q_len, is_prefill, row);
-        mb1 = visible_bits32(mrow, mask_words, col0 + 32, kv_len, q_len, is_prefill, row);
-      }
-      // pass 1: row max of my 64 columns.  bf16 rounding and the positive scale are monotone: round once.
+      if (j == 0) TC_STAMP(TS_SFULL0, 64);
+      const int col0 = (tile_lo + j) * TC_BN + q4 * 32;
+      uint32_t mb = 0xffffffffu;
+      if (col0 + 32 > kv_len) mb = visible_bits32(mrow, mask_words, col0, kv_len, q_len, is_prefill, row);
+      float v[32];
+      tmem_ld32(tmem_base + lane_addr + (uint32_t)buf * 128u + (uint32_t)q4 * 32u, v);
+      tmem_ld_wait();
+      // row max of my 32 columns; bf16 rounding and the positive scale are monotone, so round the max once
       float mx_raw = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        float v[32];
-        tmem_ld32(ts + c * 32, v);
-        tmem_ld_wait();
-        const uint32_t mb = c == 0 ? mb0 : mb1;
-        if (mb == 0xffffffffu) {                     // pure-cache chunk: no per-element mask work
+      if (mb == 0xffffffffu) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx_raw = fmaxf(mx_raw, v[i]);
-        } else {
+        for (int i = 0; i < 32; ++i) mx_raw = fmaxf(mx_raw, v[i]);
+      } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx_raw = fmaxf(mx_raw, ((mb >> i) & 1u) ? v[i] : -INFINITY);
-        }
+        for (int i = 0; i < 32; ++i) mx_raw = fmaxf(mx_raw, ((mb >> i) & 1u) ? v[i] : -INFINITY);
       }
-      float* xch = s_xch + (j & 1) * 256;            // slot parity: no write-after-read race across tiles
-      xch[half * 128 + row_l] = mx_raw;
-      named_bar_sync(1, 256);
-      mx_raw = fmaxf(mx_raw, xch[(half ^ 1) * 128 + row_l]);
-      const float mx = (mx_raw == -INFINITY) ? -INFINITY : bf16_round(bf16_round(mx_raw) * inv_sqrt_d);
-      // lazy rescale: keep the stale max while it is within 2^8 of the running max (both halves agree)
+      __nv_bfloat16* xm = s_xmax + (j & 1) * 512;   // slot parity: no write-after-read race across tiles
+      xm[q4 * 128 + row_l] = __float2bfloat16_rn(mx_raw == -INFINITY ? -INFINITY : bf16_round(mx_raw) * inv_sqrt_d);
+      named_bar_sync(1, TC_SOFTMAX_THREADS);
+      const float mx = fmaxf(fmaxf(__bfloat162float(xm[row_l]), __bfloat162float(xm[128 + row_l])),
+                             fmaxf(__bfloat162float(xm[256 + row_l]), __bfloat162float(xm[384 + row_l])));
+      // lazy rescale: keep the stale max while it is within 2^8 of the running max (all four threads agree)
       if (j == 0) {
         m_used = mx;
       } else {
@@ -327,65 +356,55 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const float m_new = fmaxf(m_used, mx);
           const float scale = (m_new == -INFINITY) ? 1.f : exp2f((m_used - m_new) * TC_LOG2E);
           l_sum *= scale;
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {              // my half of the O columns
-            float ov[32];
-            tmem_ld32(tmem_O + lane_addr + half * 64 + c * 32, ov);
-            tmem_ld_wait();
+          float ov[32];
+          tmem_ld32(tO, ov);                         // my quarter of the O columns
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) ov[i] *= scale;
-            tmem_st32(tmem_O + lane_addr + half * 64 + c * 32, ov);
-          }
+          for (int i = 0; i < 32; ++i) ov[i] *= scale;
+          tmem_st32(tO, ov);
           tmem_st_wait();
           m_used = m_new;
         }
       }
       const float off = (m_used == -INFINITY) ? 0.f : m_used * TC_LOG2E;
-      // pass 2: P = exp2(score - max) as bf16 into the K stage, K-major SWIZZLE_128B:
-      //         [kv block of 64 = my half][row][128 B], 16-byte chunk index ^ (row & 7)
-      unsigned char* prow = smem + TC_TILE_BYTES * (1 + 2 * s) + half * TC_HALF_BYTES + row_l * 128;
+      // P = exp2(score - max) as bf16 into the K stage, K-major SWIZZLE_128B:
+      //   [kv block of 64][row][128 B], 16-byte chunk index ^ (row & 7); my quarter = 4 chunks of block q4 / 2
+      unsigned char* prow = smem + TC_TILE_BYTES * (1 + 2 * s) + (q4 >> 1) * TC_HALF_BYTES + row_l * 128;
+      const bool all_vis = (mb == 0xffffffffu);
       float psum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        float v[32];
-        tmem_ld32(ts + c * 32, v);
-        tmem_ld_wait();
-        const uint32_t mb = c == 0 ? mb0 : mb1;
-        const bool all_vis = (mb == 0xffffffffu);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float p[8];
+      for (int g = 0; g < 4; ++g) {
+        float p[8];
 #pragma unroll
-          for (int e = 0; e < 8; e += 2) {
-            const int i = g * 8 + e;
-            // reference rounding points, two elements per cvt: bf16(bf16(s) * (1/sqrt(d)))
-            float2 r1 = __bfloat1622float2(__floats2bfloat162_rn(v[i], v[i + 1]));
-            float2 r2 = __bfloat1622float2(__floats2bfloat162_rn(r1.x * inv_sqrt_d, r1.y * inv_sqrt_d));
-            p[e] = ex2_approx(r2.x * TC_LOG2E - off);
-            p[e + 1] = ex2_approx(r2.y * TC_LOG2E - off);
-            if (!all_vis) {
-              if (!((mb >> i) & 1u)) p[e] = 0.f;
-              if (!((mb >> (i + 1)) & 1u)) p[e + 1] = 0.f;
-            }
-            psum += p[e] + p[e + 1];
+        for (int e = 0; e < 8; e += 2) {
+          const int i = g * 8 + e;
+          // reference rounding points, two elements per cvt: bf16(bf16(s) * (1/sqrt(d)))
+          float2 r1 = __bfloat1622float2(__floats2bfloat162_rn(v[i], v[i + 1]));
+          float2 r2 = __bfloat1622float2(__floats2bfloat162_rn(r1.x * inv_sqrt_d, r1.y * inv_sqrt_d));
+          p[e] = ex2_approx(r2.x * TC_LOG2E - off);
+          p[e + 1] = ex2_approx(r2.y * TC_LOG2E - off);
+          if (!all_vis) {
+            if (!((mb >> i) & 1u)) p[e] = 0.f;
+            if (!((mb >> (i + 1)) & 1u)) p[e + 1] = 0.f;
           }
-          uint4 pk;
-          pk.x = pack2_bf16(p[0], p[1]); pk.y = pack2_bf16(p[2], p[3]);
-          pk.z = pack2_bf16(p[4], p[5]); pk.w = pack2_bf16(p[6], p[7]);
-          const int cc = c * 4 + g;
-          *reinterpret_cast<uint4*>(prow + ((cc ^ (row_l & 7)) << 4)) = pk;
+          psum += p[e] + p[e + 1];
         }
+        uint4 pk;
+        pk.x = pack2_bf16(p[0], p[1]); pk.y = pack2_bf16(p[2], p[3]);
+        pk.z = pack2_bf16(p[4], p[5]); pk.w = pack2_bf16(p[6], p[7]);
+        const int cc = (q4 & 1) * 4 + g;
+        *reinterpret_cast<uint4*>(prow + ((cc ^ (row_l & 7)) << 4)) = pk;
       }
       l_sum += psum;
       // stale cache rows past T must not reach the PV MMA (0 * NaN): zero them in the staged V tile
       const int tile0 = (tile_lo + j) * TC_BN;
       if (tile0 + TC_BN > T) {
         mbar_wait(BAR(B_VFULL + s), (j / TC_STAGES) & 1);
-        if (tile0 + row_l >= T) {                   // V tile row == kv row; each half clears one d block
-          unsigned char* pV = smem + TC_TILE_BYTES * (2 + 2 * s) + half * TC_HALF_BYTES + row_l * 128;
+        if (tile0 + row_l >= T) {                   // V tile row == kv row; each quarter clears 64 of its 256 bytes
+          unsigned char* pV = smem + TC_TILE_BYTES * (2 + 2 * s) + (q4 >> 1) * TC_HALF_BYTES + row_l * 128 + (q4 & 1) * 64;
           const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll 1
-          for (int cc = 0; cc < 8; ++cc) *reinterpret_cast<uint4*>(pV + cc * 16) = z;
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(pV + cc * 16) = z;
         }
       }
       fence_proxy_async();
@@ -393,168 +412,127 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_arrive(BAR(B_PFULL + buf));
     }
 
-    // ---- epilogue: O (TMEM) -> final output or split partial; each half owns 64 of the 128 d columns
+    // ---- epilogue: row sums meet, O (TMEM) -> bf16 output (single split) or fp32 staging in smem (cluster merge)
     mbar_wait(BAR(B_OFINAL), 0);
     tc_fence_after();
-    named_bar_sync(1, 256);                          // s_xch is free again
-    s_xch[half * 128 + row_l] = l_sum;
-    named_bar_sync(1, 256);
-    l_sum += s_xch[(half ^ 1) * 128 + row_l];
-    const int HD = n_heads * TC_D;
-    const long long rows_pad = (long long)q_tiles * TC_BM;
-    if (n_active == 1) {
+    TC_STAMP(TS_OFINAL, 64);
+    named_bar_sync(1, TC_SOFTMAX_THREADS);          // the max-exchange slots are free again
+    s_xsum[q4 * 128 + row_l] = l_sum;
+    named_bar_sync(1, TC_SOFTMAX_THREADS);
+    l_sum = (s_xsum[row_l] + s_xsum[128 + row_l]) + (s_xsum[256 + row_l] + s_xsum[384 + row_l]);
+    float ov[32];
+    tmem_ld32(tO, ov);
+    tmem_ld_wait();
+    if (n_splits == 1) {
       const float inv = l_sum > 0.f ? 1.f / l_sum : 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        float ov[32];
-        tmem_ld32(tmem_O + lane_addr + half * 64 + c * 32, ov);
-        tmem_ld_wait();
-        if (row < q_pad) {
-          uint4* dst = reinterpret_cast<uint4*>(out + (long long)row * HD + h * TC_D + half * 64 + c * 32);
+      if (row < q_pad) {
+        uint4* dst = reinterpret_cast<uint4*>(out + (long long)row * HD + h * TC_D + q4 * 32);
 #pragma unroll
-          for (int v4 = 0; v4 < 4; ++v4) {
-            uint4 pk;
-            pk.x = pack2_bf16(ov[v4 * 8 + 0] * inv, ov[v4 * 8 + 1] * inv);
-            pk.y = pack2_bf16(ov[v4 * 8 + 2] * inv, ov[v4 * 8 + 3] * inv);
-            pk.z = pack2_bf16(ov[v4 * 8 + 4] * inv, ov[v4 * 8 + 5] * inv);
-            pk.w = pack2_bf16(ov[v4 * 8 + 6] * inv, ov[v4 * 8 + 7] * inv);
-            dst[v4] = pk;
-          }
+        for (int v4 = 0; v4 < 4; ++v4) {
+          uint4 pk;
+          pk.x = pack2_bf16(ov[v4 * 8 + 0] * inv, ov[v4 * 8 + 1] * inv);
+          pk.y = pack2_bf16(ov[v4 * 8 + 2] * inv, ov[v4 * 8 + 3] * inv);
+          pk.z = pack2_bf16(ov[v4 * 8 + 4] * inv, ov[v4 * 8 + 5] * inv);
+          pk.w = pack2_bf16(ov[v4 * 8 + 6] * inv, ov[v4 * 8 + 7] * inv);
+          dst[v4] = pk;
         }
       }
     } else {
-      float* po = part_o + (((long long)split * n_heads + h) * rows_pad + row) * TC_D + half * 64;
-      float* pml = part_ml + (((long long)split * n_heads + h) * rows_pad + row) * 2;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        float ov[32];
-        tmem_ld32(tmem_O + lane_addr + half * 64 + c * 32, ov);
-        tmem_ld_wait();
+      float* so = reinterpret_cast<float*>(smem + TC_SO_OFFSET) + row_l * TC_SO_STRIDE + q4 * 32;
 #pragma unroll
-        for (int v4 = 0; v4 < 8; ++v4)
-          reinterpret_cast<float4*>(po + c * 32)[v4] = make_float4(ov[v4 * 4], ov[v4 * 4 + 1], ov[v4 * 4 + 2], ov[v4 * 4 + 3]);
-      }
-      if (half == 0) *reinterpret_cast<float2*>(pml) = make_float2(m_used, l_sum);
+      for (int v4 = 0; v4 < 8; ++v4)
+        reinterpret_cast<float4*>(so)[v4] = make_float4(ov[v4 * 4], ov[v4 * 4 + 1], ov[v4 * 4 + 2], ov[v4 * 4 + 3]);
+      if (q4 == 0) reinterpret_cast<float2*>(smem + TC_SML_OFFSET)[row_l] = make_float2(m_used, l_sum);
     }
     tc_fence_before();
   }
 
-  // ---- teardown + split combine
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-  if (n_active == 1) return;
-  // Two ways to merge the split partials (m, l, unnormalised O):
-  //   coop  -- every CTA of the (head, q tile) group waits for its siblings and merges 1/n_active of the
-  //            rows: the merge is spread over all SMs.  Needs the whole grid co-resident (host checks
-  //            grid <= #SMs at 1 CTA/SM); the wait is bounded (trap) like every other wait here.
-  //   last  -- the last CTA to arrive merges all rows (any grid size).
-  int* cnt_arrive = &counters[2 * (h * q_tiles + mt)];
-  int* cnt_done = cnt_arrive + 1;
-  int row_lo = 0, row_hi = TC_BM;
-  if (coop) {
-    if (threadIdx.x == 0) {
-      __threadfence();                               // publish this CTA's partials (cumulative over the barrier)
-      atomicAdd(cnt_arrive, 1);
-      const long long t0 = clock64();
-      while (atomicAdd(cnt_arrive, 0) < n_active) {
-        __nanosleep(32);
-        if (clock64() - t0 > 4000000000LL) __trap();
-      }
+  // ---- teardown (TMEM) ----
+  if (active) {
+    __syncthreads();
+    if (warp == 1) {
+      tc_fence_after();
+      tmem_dealloc(tmem_base, 512);
     }
+  }
+  TC_STAMP(TS_STAGED, 0);
+  if (n_splits == 1) { TC_STAMP(TS_END, 0); return; }
+
+  // ---- split merge across the cluster through distributed shared memory ----
+  // Every CTA staged its unnormalised O (fp32) and (m, l) per row in its own smem.  After the cluster barrier,
+  // CTA c merges 1/n_active of the rows: weights w_s = 2^(m_s - m) / sum_s l_s 2^(m_s - m), out = sum_s w_s O_s.
+  cluster_arrive();
+  cluster_wait();
+  TC_STAMP(TS_CLUSTER, 0);
+  if (active) {
     const int per = (TC_BM + n_active - 1) / n_active;
-    row_lo = split * per;
-    row_hi = min(TC_BM, row_lo + per);
-  } else {
-    if (threadIdx.x == 0) {
-      __threadfence();
-      *s_flag = (atomicAdd(cnt_arrive, 1) == n_active - 1);
+    const int row_lo = split * per;
+    const int n_rows = max(0, min(TC_BM, row_lo + per) - row_lo);
+    float* s_w = reinterpret_cast<float*>(smem + TC_SW_OFFSET);
+    const uint32_t sml_a = sQ_a + TC_SML_OFFSET, so_a = sQ_a + TC_SO_OFFSET;
+    for (int r = threadIdx.x; r < n_rows; r += TC_THREADS) {
+      float2 ml[8];
+      float mmax = -INFINITY;
+#pragma unroll
+      for (int sp = 0; sp < 8; ++sp) {
+        ml[sp] = sp < n_active ? ld_dsmem_f2(dsmem_addr(sml_a + (uint32_t)(row_lo + r) * 8u, sp)) : make_float2(-INFINITY, 0.f);
+        mmax = fmaxf(mmax, ml[sp].x);
+      }
+      float lsum = 0.f, wv[8];
+#pragma unroll
+      for (int sp = 0; sp < 8; ++sp) {
+        wv[sp] = (ml[sp].x == -INFINITY) ? 0.f : exp2f((ml[sp].x - mmax) * TC_LOG2E);
+        lsum += ml[sp].y * wv[sp];
+      }
+      const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
+#pragma unroll
+      for (int sp = 0; sp < 8; ++sp) s_w[r * 8 + sp] = wv[sp] * inv;
     }
     __syncthreads();
-    if (!*s_flag) return;
-  }
-  __syncthreads();
-  const int HD = n_heads * TC_D;
-  const long long rows_pad = (long long)q_tiles * TC_BM;
-  // phase A: per-row merge weights w_s = 2^(m_s - m) / sum_s l_s 2^(m_s - m)  -> smem (the Q tile is dead).
-  // Every load of the merge is independent of the others: one (row, split) pair per thread here, unrolled
-  // batches below, so the L2 latency is paid once, not once per split.
-  const int n_rows = row_hi - row_lo;
-  float* s_w = reinterpret_cast<float*>(smem);                 // [n_rows][n_active] weights
-  float2* s_ml = reinterpret_cast<float2*>(smem + TC_TILE_BYTES);   // [n_rows][n_active] (m, l), dead K/V stage 0
-  for (int i = threadIdx.x; i < n_rows * n_active; i += TC_THREADS) {
-    const int rl = row_lo + i / n_active, sp = i % n_active;
-    s_ml[i] = __ldcg(reinterpret_cast<const float2*>(part_ml + ((((long long)sp * n_heads + h) * rows_pad) + mt * TC_BM + rl) * 2));
-  }
-  __syncthreads();
-  for (int r = threadIdx.x; r < n_rows; r += TC_THREADS) {
-    float mmax = -INFINITY;
-    for (int sp = 0; sp < n_active; ++sp) mmax = fmaxf(mmax, s_ml[r * n_active + sp].x);
-    float lsum = 0.f;
-    for (int sp = 0; sp < n_active; ++sp) {
-      const float2 ml = s_ml[r * n_active + sp];
-      const float wgt = (ml.x == -INFINITY) ? 0.f : exp2f((ml.x - mmax) * TC_LOG2E);
-      s_w[r * n_active + sp] = wgt;
-      lsum += ml.y * wgt;
-    }
-    const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
-    for (int sp = 0; sp < n_active; ++sp) s_w[r * n_active + sp] *= inv;
-  }
-  __syncthreads();
-  // phase B: out[row] = sum_s w_s O_s[row], four items per thread per round, up to 8 splits per batch in flight
-  const int n_items = n_rows * (TC_D / 4);
-  const float* po_h = part_o + ((long long)h * rows_pad + mt * TC_BM) * TC_D;
-  const long long split_stride = (long long)n_heads * rows_pad * TC_D;
-  for (int base = 0; base < n_items; base += TC_THREADS * 4) {
-    float4 acc[4];
+    // item = (row, 8 columns): two float4 per split, all loads independent
+    const int n_items = n_rows * (TC_D / 8);
+    for (int idx = threadIdx.x; idx < n_items; idx += TC_THREADS) {
+      const int r = idx / (TC_D / 8), c8 = idx % (TC_D / 8);
+      const uint32_t a0 = so_a + (uint32_t)((row_lo + r) * TC_SO_STRIDE + c8 * 8) * 4u;
+      float4 va[8], vb[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s0 = 0; s0 < n_active; s0 += 8) {
-      float4 v[4][8];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int idx = base + k * TC_THREADS + threadIdx.x;
-        const int rl = row_lo + idx / (TC_D / 4), c4 = idx % (TC_D / 4);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const bool ok = idx < n_items && (s0 + u) < n_active;
-          v[k][u] = ok ? __ldcg(reinterpret_cast<const float4*>(po_h + (long long)(s0 + u) * split_stride + (long long)rl * TC_D + c4 * 4))
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int sp = 0; sp < 8; ++sp) {
+        if (sp < n_active) {
+          const uint32_t ra = dsmem_addr(a0, sp);
+          va[sp] = ld_dsmem_f4(ra);
+          vb[sp] = ld_dsmem_f4(ra + 16);
+        } else {
+          va[sp] = make_float4(0.f, 0.f, 0.f, 0.f);
+          vb[sp] = va[sp];
         }
       }
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int idx = base + k * TC_THREADS + threadIdx.x;
-        const int r = idx / (TC_D / 4);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float wgt = (idx < n_items && (s0 + u) < n_active) ? s_w[r * n_active + s0 + u] : 0.f;
-          acc[k].x += v[k][u].x * wgt; acc[k].y += v[k][u].y * wgt; acc[k].z += v[k][u].z * wgt; acc[k].w += v[k][u].w * wgt;
-        }
+      for (int sp = 0; sp < 8; ++sp) {
+        const float wgt = s_w[r * 8 + sp];
+        a.x += va[sp].x * wgt; a.y += va[sp].y * wgt; a.z += va[sp].z * wgt; a.w += va[sp].w * wgt;
+        b.x += vb[sp].x * wgt; b.y += vb[sp].y * wgt; b.z += vb[sp].z * wgt; b.w += vb[sp].w * wgt;
+      }
+      const int row = mt * TC_BM + row_lo + r;
+      if (row < q_pad) {
+        uint4 pk;
+        pk.x = pack2_bf16(a.x, a.y); pk.y = pack2_bf16(a.z, a.w);
+        pk.z = pack2_bf16(b.x, b.y); pk.w = pack2_bf16(b.z, b.w);
+        *reinterpret_cast<uint4*>(out + (long long)row * HD + h * TC_D + c8 * 8) = pk;
       }
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int idx = base + k * TC_THREADS + threadIdx.x;
-      if (idx >= n_items) continue;
-      const int rl = row_lo + idx / (TC_D / 4), c4 = idx % (TC_D / 4);
-      const int row = mt * TC_BM + rl;
-      if (row >= q_pad) continue;
-      uint2 pk;
-      pk.x = pack2_bf16(acc[k].x, acc[k].y);
-      pk.y = pack2_bf16(acc[k].z, acc[k].w);
-      *reinterpret_cast<uint2*>(out + (long long)row * HD + h * TC_D + c4 * 4) = pk;
-    }
   }
-  // counters return to zero once every participant is through
-  if (coop) {
-    __syncthreads();
-    if (threadIdx.x == 0 && atomicAdd(cnt_done, 1) == n_active - 1) { *cnt_arrive = 0; *cnt_done = 0; __threadfence(); }
-  } else if (threadIdx.x == 0) {
-    *cnt_arrive = 0;
-  }
+  TC_STAMP(TS_MERGED, 0);
+  cluster_arrive();      // nobody may exit while a sibling still reads its shared memory
+  cluster_wait();
+  TC_STAMP(TS_END, 0);
+}
+
+int attn_tc_set_timing_buffer(void* dev_ptr) {
+  long long* p = reinterpret_cast<long long*>(dev_ptr);
+  cudaError_t e = cudaMemcpyToSymbol(g_attn_timing, &p, sizeof(p));
+  if (e != cudaSuccess) { set_cuda_error(e, "cudaMemcpyToSymbol(g_attn_timing)"); return LADE_ECUDA; }
+  return LADE_OK;
 }
 
 // ---- host: tensor maps ----------------------------------------------------------------------------------
@@ -615,10 +593,10 @@ int attn_fwd_tc_launch(cudaStream_t stream, const void* q, const void* k_cache, 
                        const uint32_t* rowmask, int mask_words, const int32_t* meta, void* scratch, int q_pad, int n_heads,
                        int n_kv_heads, int head_dim, int kv_capacity, int kv_bound, int n_splits) {
   (void)kv_bound;
+  (void)scratch;   // split partials never leave the SMs on this path (cluster / DSMEM merge)
   if (head_dim != TC_D) return LADE_EUNSUPPORTED;
   const int q_tiles = (q_pad + TC_BM - 1) / TC_BM;
-  if ((long long)n_heads * q_tiles * 2 > TC_MAX_COUNTERS) return LADE_EUNSUPPORTED;
-  if (n_splits > 64) n_splits = 64;   // merge weights live in the 32 KB Q tile: 128 rows x 64 splits
+  if (n_splits > 8) n_splits = 8;   // portable cluster size
   if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(k_cache) & 15) ||
       (reinterpret_cast<uintptr_t>(v_cache) & 15))
     return LADE_EINVAL;
@@ -632,23 +610,22 @@ int attn_fwd_tc_launch(cudaStream_t stream, const void* q, const void* k_cache, 
     LADE_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     attr_set = true;
   }
-  const long long rows_pad = (long long)q_tiles * TC_BM;
-  int* counters = reinterpret_cast<int*>(scratch);
-  float* part_ml = reinterpret_cast<float*>(counters + TC_MAX_COUNTERS);
-  float* part_o = part_ml + (long long)n_splits * n_heads * rows_pad * 2;
-  dim3 grid(n_splits, n_heads, q_tiles);
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    LADE_CUDA_CHECK(cudaGetDevice(&dev));
-    LADE_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  // cooperative merge only when every CTA of the launch is resident at once (1 CTA/SM kernel)
-  const int coop = ((long long)n_splits * n_heads * q_tiles <= num_sms) ? 1 : 0;
-  attn_fwd_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(
-      tmQ, tmK, tmV, (__nv_bfloat16*)out, rowmask, mask_words, meta, part_o, part_ml, counters, q_pad, n_heads, n_kv_heads, n_splits,
-      1.0f / sqrtf((float)head_dim), coop);
-  LADE_LAUNCH_CHECK("attn_fwd_tc_kernel");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n_splits, n_heads, q_tiles);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;   // the splits of one (head, q tile) form a cluster
+  attr[0].val.clusterDim.x = n_splits;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const float inv_sqrt_d = 1.0f / sqrtf((float)head_dim);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_fwd_tc_kernel, tmQ, tmK, tmV, (__nv_bfloat16*)out, rowmask, mask_words, meta,
+                                     q_pad, n_heads, n_kv_heads, n_splits, inv_sqrt_d);
+  if (e != cudaSuccess) { set_cuda_error(e, "cudaLaunchKernelEx(attn_fwd_tc_kernel)"); return LADE_ECUDA; }
   return LADE_OK;
 }
 

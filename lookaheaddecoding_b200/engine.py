@@ -106,7 +106,7 @@ class LookaheadEngine:
         sm = torch.cuda.get_device_properties(self.dev).multi_processor_count
         q_tiles = (self.q_steady + 127) // 128
         # one CTA per SM (TMEM/smem bound): keep the split grid within a single wave
-        self.attn_splits = int(attn_splits) if attn_splits else max(1, min(64, sm // (self.nh * q_tiles)))
+        self.attn_splits = int(attn_splits) if attn_splits else max(1, min(8, sm // (self.nh * q_tiles)))   # <= 8: the splits of a head form a thread-block cluster
 
         self._fuse_weights()
         self._rope_tables()

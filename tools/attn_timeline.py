@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""Per-CTA phase timeline of the tcgen05 attention kernel (lade_debug_attn_timing)."""
+import os, sys, json
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from lookaheaddecoding_b200 import _cabi
+from attn_microbench import steady_rowmask
+
+lib = _cabi.load()
+H, D, L = 32, 128, 8
+for kv, ns in [(1024, 4), (1024, 1), (3072, 4)]:
+    rm_np, mw, q_len = steady_rowmask(15, 5, 15)
+    cap = kv + q_len + 64
+    kvc = torch.randn(L, 2, H, cap, D, device="cuda", dtype=torch.bfloat16)
+    q = torch.randn(H, q_len, D, device="cuda", dtype=torch.bfloat16)
+    out = torch.empty(q_len, H * D, device="cuda", dtype=torch.bfloat16)
+    rd = torch.from_numpy(rm_np).cuda()
+    meta = torch.zeros(_cabi.META_INTS, dtype=torch.int32, device="cuda")
+    for k, v in {_cabi.M_Q_LEN: q_len, _cabi.M_KV_LEN: kv, _cabi.M_N_INPUT: 1, _cabi.M_PHASE: 2, _cabi.M_Q_PAD: q_len}.items():
+        meta[k] = v
+    scratch = torch.zeros(lib.lade_attn_scratch_bytes(q_len, H, D, ns), dtype=torch.uint8, device="cuda")
+    tb = torch.zeros(ns * H * 8, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    def run(l):
+        _cabi.check(lib.lade_attn_fwd(st, q.data_ptr(), kvc[l, 0].data_ptr(), kvc[l, 1].data_ptr(), out.data_ptr(), rd.data_ptr(), mw,
+                                      meta.data_ptr(), scratch.data_ptr(), q_len, H, H, D, cap, kv + q_len, ns, 2))
+    for l in range(L): run(l)
+    torch.cuda.synchronize()
+    _cabi.check(lib.lade_debug_attn_timing(tb.data_ptr()))
+    run(0)
+    torch.cuda.synchronize()
+    _cabi.check(lib.lade_debug_attn_timing(0))
+    t = tb.cpu().numpy().reshape(-1, 8).astype(np.float64)
+    t = t[t[:, 0] > 0]
+    names = ["start", "kfull0", "sfull0", "ofinal", "staged", "cluster", "merged", "end"]
+    rel = (t - t[:, :1]) / 1.965e3     # us at 1965 MHz
+    print(json.dumps({"kv": kv, "splits": ns, "ctas": int(len(t)),
+                      "median_us_since_start": {n: round(float(np.median(rel[:, i])), 2) for i, n in enumerate(names)},
+                      "max_us_since_start": {n: round(float(np.max(rel[:, i])), 2) for i, n in enumerate(names)}}))
