@@ -223,7 +223,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if ((sQ_a & 1023u) != 0) __trap();   // SWIZZLE_128B tiles need 1024-byte alignment
       mbar_init(BAR(B_QFULL), 1);
       for (int s = 0; s < TC_STAGES; ++s) { mbar_init(BAR(B_KFULL + s), 1); mbar_init(BAR(B_VFULL + s), 1); mbar_init(BAR(B_FREE + s), 1); }
-      for (int b = 0; b < 2; ++b) { mbar_init(BAR(B_SFULL + b), 1); mbar_init(BAR(B_PFULL + b), TC_SOFTMAX_THREADS); }
+      for (int b = 0; b < 2; ++b) { mbar_init(BAR(B_SFULL + b), 1); mbar_init(BAR(B_PFULL + b), TC_SOFTMAX_THREADS / 32); }
       mbar_init(BAR(B_OFINAL), 1);
       fence_barrier_init();
       // start the memory stream before anything else: Q and the first STAGES K/V tiles are in flight while the
@@ -332,14 +332,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tmem_ld32(tmem_base + lane_addr + (uint32_t)buf * 128u + (uint32_t)q4 * 32u, v);
       tmem_ld_wait();
       // row max of my 32 columns; bf16 rounding and the positive scale are monotone, so round the max once
-      float mx_raw = -INFINITY;
+      float mq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
       if (mb == 0xffffffffu) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx_raw = fmaxf(mx_raw, v[i]);
+        for (int i = 0; i < 32; ++i) mq[i & 3] = fmaxf(mq[i & 3], v[i]);
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx_raw = fmaxf(mx_raw, ((mb >> i) & 1u) ? v[i] : -INFINITY);
+        for (int i = 0; i < 32; ++i) mq[i & 3] = fmaxf(mq[i & 3], ((mb >> i) & 1u) ? v[i] : -INFINITY);
       }
+      const float mx_raw = fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3]));
       __nv_bfloat16* xm = s_xmax + (j & 1) * 512;   // slot parity: no write-after-read race across tiles
       xm[q4 * 128 + row_l] = __float2bfloat16_rn(mx_raw == -INFINITY ? -INFINITY : bf16_round(mx_raw) * inv_sqrt_d);
       named_bar_sync(1, TC_SOFTMAX_THREADS);
@@ -371,7 +372,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       //   [kv block of 64][row][128 B], 16-byte chunk index ^ (row & 7); my quarter = 4 chunks of block q4 / 2
       unsigned char* prow = smem + TC_TILE_BYTES * (1 + 2 * s) + (q4 >> 1) * TC_HALF_BYTES + row_l * 128;
       const bool all_vis = (mb == 0xffffffffu);
-      float psum = 0.f;
+      float ps4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         float p[8];
@@ -387,7 +388,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             if (!((mb >> i) & 1u)) p[e] = 0.f;
             if (!((mb >> (i + 1)) & 1u)) p[e + 1] = 0.f;
           }
-          psum += p[e] + p[e + 1];
+          ps4[g] += p[e] + p[e + 1];
         }
         uint4 pk;
         pk.x = pack2_bf16(p[0], p[1]); pk.y = pack2_bf16(p[2], p[3]);
@@ -395,7 +396,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int cc = (q4 & 1) * 4 + g;
         *reinterpret_cast<uint4*>(prow + ((cc ^ (row_l & 7)) << 4)) = pk;
       }
-      l_sum += psum;
+      l_sum += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
       // stale cache rows past T must not reach the PV MMA (0 * NaN): zero them in the staged V tile
       const int tile0 = (tile_lo + j) * TC_BN;
       if (tile0 + TC_BN > T) {
@@ -407,9 +408,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(pV + cc * 16) = z;
         }
       }
-      fence_proxy_async();
+      fence_proxy_async();                         // my P / V writes -> visible to the tensor core's async proxy
       tc_fence_before();
-      mbar_arrive(BAR(B_PFULL + buf));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(B_PFULL + buf));   // one arrival per warp (16), not 512 smem atomics
     }
 
     // ---- epilogue: row sums meet, O (TMEM) -> bf16 output (single split) or fp32 staging in smem (cluster merge)
@@ -468,37 +470,22 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int per = (TC_BM + n_active - 1) / n_active;
     const int row_lo = split * per;
     const int n_rows = max(0, min(TC_BM, row_lo + per) - row_lo);
-    float* s_w = reinterpret_cast<float*>(smem + TC_SW_OFFSET);
     const uint32_t sml_a = sQ_a + TC_SML_OFFSET, so_a = sQ_a + TC_SO_OFFSET;
-    for (int r = threadIdx.x; r < n_rows; r += TC_THREADS) {
-      float2 ml[8];
-      float mmax = -INFINITY;
-#pragma unroll
-      for (int sp = 0; sp < 8; ++sp) {
-        ml[sp] = sp < n_active ? ld_dsmem_f2(dsmem_addr(sml_a + (uint32_t)(row_lo + r) * 8u, sp)) : make_float2(-INFINITY, 0.f);
-        mmax = fmaxf(mmax, ml[sp].x);
-      }
-      float lsum = 0.f, wv[8];
-#pragma unroll
-      for (int sp = 0; sp < 8; ++sp) {
-        wv[sp] = (ml[sp].x == -INFINITY) ? 0.f : exp2f((ml[sp].x - mmax) * TC_LOG2E);
-        lsum += ml[sp].y * wv[sp];
-      }
-      const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
-#pragma unroll
-      for (int sp = 0; sp < 8; ++sp) s_w[r * 8 + sp] = wv[sp] * inv;
-    }
-    __syncthreads();
-    // item = (row, 8 columns): two float4 per split, all loads independent
+    // item = (row, 8 columns).  A thread issues the loads of an item together -- (m, l) of every split and the two
+    // float4 of the first four splits, all independent -- so the DSMEM latency is paid once per item.
     const int n_items = n_rows * (TC_D / 8);
     for (int idx = threadIdx.x; idx < n_items; idx += TC_THREADS) {
       const int r = idx / (TC_D / 8), c8 = idx % (TC_D / 8);
-      const uint32_t a0 = so_a + (uint32_t)((row_lo + r) * TC_SO_STRIDE + c8 * 8) * 4u;
-      float4 va[8], vb[8];
+      const uint32_t ml_a = sml_a + (uint32_t)(row_lo + r) * 8u;
+      const uint32_t o_a = so_a + (uint32_t)((row_lo + r) * TC_SO_STRIDE + c8 * 8) * 4u;
+      float2 ml[8];
+      float4 va[4], vb[4];
 #pragma unroll
-      for (int sp = 0; sp < 8; ++sp) {
+      for (int sp = 0; sp < 8; ++sp) ml[sp] = sp < n_active ? ld_dsmem_f2(dsmem_addr(ml_a, sp)) : make_float2(-INFINITY, 0.f);
+#pragma unroll
+      for (int sp = 0; sp < 4; ++sp) {
         if (sp < n_active) {
-          const uint32_t ra = dsmem_addr(a0, sp);
+          const uint32_t ra = dsmem_addr(o_a, sp);
           va[sp] = ld_dsmem_f4(ra);
           vb[sp] = ld_dsmem_f4(ra + 16);
         } else {
@@ -506,18 +493,45 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           vb[sp] = va[sp];
         }
       }
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      float mmax = -INFINITY;
+#pragma unroll
+      for (int sp = 0; sp < 8; ++sp) mmax = fmaxf(mmax, ml[sp].x);
+      float wv[8], lsum = 0.f;
 #pragma unroll
       for (int sp = 0; sp < 8; ++sp) {
-        const float wgt = s_w[r * 8 + sp];
-        a.x += va[sp].x * wgt; a.y += va[sp].y * wgt; a.z += va[sp].z * wgt; a.w += va[sp].w * wgt;
-        b.x += vb[sp].x * wgt; b.y += vb[sp].y * wgt; b.z += vb[sp].z * wgt; b.w += vb[sp].w * wgt;
+        wv[sp] = (ml[sp].x == -INFINITY) ? 0.f : exp2f((ml[sp].x - mmax) * TC_LOG2E);
+        lsum += ml[sp].y * wv[sp];
       }
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+#pragma unroll
+      for (int sp = 0; sp < 4; ++sp) {
+        a.x += va[sp].x * wv[sp]; a.y += va[sp].y * wv[sp]; a.z += va[sp].z * wv[sp]; a.w += va[sp].w * wv[sp];
+        b.x += vb[sp].x * wv[sp]; b.y += vb[sp].y * wv[sp]; b.z += vb[sp].z * wv[sp]; b.w += vb[sp].w * wv[sp];
+      }
+      if (n_active > 4) {
+#pragma unroll
+        for (int sp = 4; sp < 8; ++sp) {
+          if (sp < n_active) {
+            const uint32_t ra = dsmem_addr(o_a, sp);
+            va[sp - 4] = ld_dsmem_f4(ra);
+            vb[sp - 4] = ld_dsmem_f4(ra + 16);
+          } else {
+            va[sp - 4] = make_float4(0.f, 0.f, 0.f, 0.f);
+            vb[sp - 4] = va[sp - 4];
+          }
+        }
+#pragma unroll
+        for (int sp = 4; sp < 8; ++sp) {
+          a.x += va[sp - 4].x * wv[sp]; a.y += va[sp - 4].y * wv[sp]; a.z += va[sp - 4].z * wv[sp]; a.w += va[sp - 4].w * wv[sp];
+          b.x += vb[sp - 4].x * wv[sp]; b.y += vb[sp - 4].y * wv[sp]; b.z += vb[sp - 4].z * wv[sp]; b.w += vb[sp - 4].w * wv[sp];
+        }
+      }
+      const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
       const int row = mt * TC_BM + row_lo + r;
       if (row < q_pad) {
         uint4 pk;
-        pk.x = pack2_bf16(a.x, a.y); pk.y = pack2_bf16(a.z, a.w);
-        pk.z = pack2_bf16(b.x, b.y); pk.w = pack2_bf16(b.z, b.w);
+        pk.x = pack2_bf16(a.x * inv, a.y * inv); pk.y = pack2_bf16(a.z * inv, a.w * inv);
+        pk.z = pack2_bf16(b.x * inv, b.y * inv); pk.w = pack2_bf16(b.z * inv, b.w * inv);
         *reinterpret_cast<uint4*>(out + (long long)row * HD + h * TC_D + c8 * 8) = pk;
       }
     }
