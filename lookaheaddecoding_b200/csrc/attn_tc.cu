@@ -147,8 +147,10 @@ __device__ __forceinline__ unsigned pack2_bf16(float lo, float hi) {
   return *reinterpret_cast<unsigned*>(&v);
 }
 
-// Optional per-CTA phase timestamps (clock64) for profiling the kernel's own timeline: 8 slots per CTA.
+// Optional per-CTA phase timestamps (clock64) for profiling the kernel's own timeline: 16 slots per CTA
+// (0-7 CTA phases, 8-15 the softmax phases of tile 1 as seen by thread 64).
 __device__ long long* g_attn_timing = nullptr;
+__device__ int g_attn_variant = 0;   // profiling experiments only (tools/attn_timeline.py); 0 = production numerics
 #define TC_STAMP(slot, tid) do { if (tbuf && threadIdx.x == (tid)) tbuf[slot] = clock64(); } while (0)
 enum { TS_START = 0, TS_KFULL0 = 1, TS_SFULL0 = 2, TS_OFINAL = 3, TS_STAGED = 4, TS_CLUSTER = 5, TS_MERGED = 6, TS_END = 7 };
 
@@ -201,7 +203,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int my_tiles = active ? min(n_tiles, tile_lo + tps) - tile_lo : 0;
   const int hk = h / (n_heads / n_kv_heads);
   const int HD = n_heads * TC_D;
-  long long* tbuf = g_attn_timing ? g_attn_timing + 8ll * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
+  long long* tbuf = g_attn_timing ? g_attn_timing + 16ll * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
   TC_STAMP(TS_START, 0);
 
   unsigned char* sQ = smem;
@@ -320,17 +322,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const uint32_t tO = tmem_O + lane_addr + (uint32_t)q4 * 32u;
     float m_used = -INFINITY, l_sum = 0.f;
+    const int variant = g_attn_variant;
     for (int j = 0; j < my_tiles; ++j) {
       const int buf = j & 1, s = j % TC_STAGES;
+      if (j == 1) TC_STAMP(8, 64);
       mbar_wait(BAR(B_SFULL + buf), (j >> 1) & 1);
       tc_fence_after();
       if (j == 0) TC_STAMP(TS_SFULL0, 64);
+      if (j == 1) TC_STAMP(9, 64);
       const int col0 = (tile_lo + j) * TC_BN + q4 * 32;
       uint32_t mb = 0xffffffffu;
       if (col0 + 32 > kv_len) mb = visible_bits32(mrow, mask_words, col0, kv_len, q_len, is_prefill, row);
       float v[32];
       tmem_ld32(tmem_base + lane_addr + (uint32_t)buf * 128u + (uint32_t)q4 * 32u, v);
       tmem_ld_wait();
+      if (j == 1) TC_STAMP(10, 64);
       // row max of my 32 columns; bf16 rounding and the positive scale are monotone, so round the max once
       float mq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
       if (mb == 0xffffffffu) {
@@ -343,7 +349,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const float mx_raw = fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3]));
       __nv_bfloat16* xm = s_xmax + (j & 1) * 512;   // slot parity: no write-after-read race across tiles
       xm[q4 * 128 + row_l] = __float2bfloat16_rn(mx_raw == -INFINITY ? -INFINITY : bf16_round(mx_raw) * inv_sqrt_d);
+      if (j == 1) TC_STAMP(11, 64);
       named_bar_sync(1, TC_SOFTMAX_THREADS);
+      if (j == 1) TC_STAMP(12, 64);
       const float mx = fmaxf(fmaxf(__bfloat162float(xm[row_l]), __bfloat162float(xm[128 + row_l])),
                              fmaxf(__bfloat162float(xm[256 + row_l]), __bfloat162float(xm[384 + row_l])));
       // lazy rescale: keep the stale max while it is within 2^8 of the running max (all four threads agree)
@@ -380,10 +388,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int e = 0; e < 8; e += 2) {
           const int i = g * 8 + e;
           // reference rounding points, two elements per cvt: bf16(bf16(s) * (1/sqrt(d)))
-          float2 r1 = __bfloat1622float2(__floats2bfloat162_rn(v[i], v[i + 1]));
-          float2 r2 = __bfloat1622float2(__floats2bfloat162_rn(r1.x * inv_sqrt_d, r1.y * inv_sqrt_d));
-          p[e] = ex2_approx(r2.x * TC_LOG2E - off);
-          p[e + 1] = ex2_approx(r2.y * TC_LOG2E - off);
+          float2 r1 = (variant & 2) ? make_float2(v[i], v[i + 1]) : __bfloat1622float2(__floats2bfloat162_rn(v[i], v[i + 1]));
+          float2 r2 = (variant & 1) ? make_float2(r1.x * inv_sqrt_d, r1.y * inv_sqrt_d)
+                                    : __bfloat1622float2(__floats2bfloat162_rn(r1.x * inv_sqrt_d, r1.y * inv_sqrt_d));
+          if (variant & 4) {
+            p[e] = r2.x * TC_LOG2E - off;
+            p[e + 1] = r2.y * TC_LOG2E - off;
+          } else {
+            p[e] = ex2_approx(r2.x * TC_LOG2E - off);
+            p[e + 1] = ex2_approx(r2.y * TC_LOG2E - off);
+          }
           if (!all_vis) {
             if (!((mb >> i) & 1u)) p[e] = 0.f;
             if (!((mb >> (i + 1)) & 1u)) p[e + 1] = 0.f;
@@ -397,6 +411,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         *reinterpret_cast<uint4*>(prow + ((cc ^ (row_l & 7)) << 4)) = pk;
       }
       l_sum += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
+      if (j == 1) TC_STAMP(13, 64);
       // stale cache rows past T must not reach the PV MMA (0 * NaN): zero them in the staged V tile
       const int tile0 = (tile_lo + j) * TC_BN;
       if (tile0 + TC_BN > T) {
@@ -410,8 +425,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       fence_proxy_async();                         // my P / V writes -> visible to the tensor core's async proxy
       tc_fence_before();
+      if (j == 1) TC_STAMP(14, 64);
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(B_PFULL + buf));   // one arrival per warp (16), not 512 smem atomics
+      if (j == 1) TC_STAMP(15, 64);
     }
 
     // ---- epilogue: row sums meet, O (TMEM) -> bf16 output (single split) or fp32 staging in smem (cluster merge)
@@ -540,6 +557,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   cluster_arrive();      // nobody may exit while a sibling still reads its shared memory
   cluster_wait();
   TC_STAMP(TS_END, 0);
+}
+
+int attn_tc_set_variant(int v) {
+  cudaError_t e = cudaMemcpyToSymbol(g_attn_variant, &v, sizeof(v));
+  if (e != cudaSuccess) { set_cuda_error(e, "cudaMemcpyToSymbol(g_attn_variant)"); return LADE_ECUDA; }
+  return LADE_OK;
 }
 
 int attn_tc_set_timing_buffer(void* dev_ptr) {

@@ -10,7 +10,9 @@ from attn_microbench import steady_rowmask
 
 lib = _cabi.load()
 H, D, L = 32, 128, 8
-for kv, ns in [(1024, 4), (1024, 1), (3072, 4)]:
+import itertools
+for (kv, ns), variant in itertools.product([(3072, 4)], [0, 1, 3, 4, 7]):
+    _cabi.check(lib.lade_debug_attn_variant(variant))
     rm_np, mw, q_len = steady_rowmask(15, 5, 15)
     cap = kv + q_len + 64
     kvc = torch.randn(L, 2, H, cap, D, device="cuda", dtype=torch.bfloat16)
@@ -21,7 +23,7 @@ for kv, ns in [(1024, 4), (1024, 1), (3072, 4)]:
     for k, v in {_cabi.M_Q_LEN: q_len, _cabi.M_KV_LEN: kv, _cabi.M_N_INPUT: 1, _cabi.M_PHASE: 2, _cabi.M_Q_PAD: q_len}.items():
         meta[k] = v
     scratch = torch.zeros(lib.lade_attn_scratch_bytes(q_len, H, D, ns), dtype=torch.uint8, device="cuda")
-    tb = torch.zeros(ns * H * 8, dtype=torch.int64, device="cuda")
+    tb = torch.zeros(ns * H * 16, dtype=torch.int64, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     def run(l):
         _cabi.check(lib.lade_attn_fwd(st, q.data_ptr(), kvc[l, 0].data_ptr(), kvc[l, 1].data_ptr(), out.data_ptr(), rd.data_ptr(), mw,
@@ -32,10 +34,11 @@ for kv, ns in [(1024, 4), (1024, 1), (3072, 4)]:
     run(0)
     torch.cuda.synchronize()
     _cabi.check(lib.lade_debug_attn_timing(0))
-    t = tb.cpu().numpy().reshape(-1, 8).astype(np.float64)
+    t = tb.cpu().numpy().reshape(-1, 16).astype(np.float64)
     t = t[t[:, 0] > 0]
-    names = ["start", "kfull0", "sfull0", "ofinal", "staged", "cluster", "merged", "end"]
+    names = ["start", "kfull0", "sfull0", "ofinal", "staged", "cluster", "merged", "end", "t1_begin", "t1_sfull", "t1_ld", "t1_max", "t1_bar", "t1_exp", "t1_fence", "t1_arrive"]
     rel = (t - t[:, :1]) / 1.965e3     # us at 1965 MHz
-    print(json.dumps({"kv": kv, "splits": ns, "ctas": int(len(t)),
+    print(json.dumps({"variant": variant, "kv": kv, "splits": ns, "ctas": int(len(t)),
                       "median_us_since_start": {n: round(float(np.median(rel[:, i])), 2) for i, n in enumerate(names)},
-                      "max_us_since_start": {n: round(float(np.max(rel[:, i])), 2) for i, n in enumerate(names)}}))
+                      }))
+_cabi.check(lib.lade_debug_attn_variant(0))
