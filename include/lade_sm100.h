@@ -166,8 +166,6 @@ int64_t lade_attn_scratch_bytes(int32_t q_pad, int32_t n_heads, int32_t head_dim
  * clock64() at its phase boundaries (start, first K tile landed, first S ready, O final, partials written,
  * siblings arrived, merged, end). */
 int lade_debug_attn_timing(void* dev_buffer);
-/* Profiling aid: numerics-altering experiment switches of the tcgen05 kernel (0 = production). */
-int lade_debug_attn_variant(int32_t variant);
 
 /* act = bf16(silu(gate)) * up on the fused [rows][2*inter] projection.  LlamaMLP, modeling_llama.py:378. */
 int lade_swiglu(void* stream, const void* gate_up, void* out, int32_t rows, int32_t inter);

@@ -46,7 +46,6 @@ _SIGNATURES = {
     "lade_attn_fwd": (C.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_p, c_p] + [c_i32] * 8),
     "lade_attn_scratch_bytes": (C.c_int64, [c_i32, c_i32, c_i32, c_i32]),
     "lade_debug_attn_timing": (C.c_int, [c_p]),
-    "lade_debug_attn_variant": (C.c_int, [c_i32]),
     "lade_swiglu": (C.c_int, [c_p, c_p, c_p, c_i32, c_i32]),
     "lade_argmax_rows": (C.c_int, [c_p, c_p, c_i32, c_i32, c_i32, c_p]),
     "lade_accept_update": (C.c_int, [c_p, c_p, c_p, c_p, c_p]),

@@ -150,7 +150,6 @@ __device__ __forceinline__ unsigned pack2_bf16(float lo, float hi) {
 // Optional per-CTA phase timestamps (clock64) for profiling the kernel's own timeline: 16 slots per CTA
 // (0-7 CTA phases, 8-15 the softmax phases of tile 1 as seen by thread 64).
 __device__ long long* g_attn_timing = nullptr;
-__device__ int g_attn_variant = 0;   // profiling experiments only (tools/attn_timeline.py); 0 = production numerics
 #define TC_STAMP(slot, tid) do { if (tbuf && threadIdx.x == (tid)) tbuf[slot] = clock64(); } while (0)
 enum { TS_START = 0, TS_KFULL0 = 1, TS_SFULL0 = 2, TS_OFINAL = 3, TS_STAGED = 4, TS_CLUSTER = 5, TS_MERGED = 6, TS_END = 7 };
 
@@ -322,7 +321,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const uint32_t tO = tmem_O + lane_addr + (uint32_t)q4 * 32u;
     float m_used = -INFINITY, l_sum = 0.f;
-    const int variant = g_attn_variant;
     for (int j = 0; j < my_tiles; ++j) {
       const int buf = j & 1, s = j % TC_STAGES;
       if (j == 1) TC_STAMP(8, 64);
@@ -339,7 +337,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (j == 1) TC_STAMP(10, 64);
       // row max of my 32 columns; bf16 rounding and the positive scale are monotone, so round the max once
       float mq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
-      if (mb == 0xffffffffu) {
+      if (__all_sync(0xffffffffu, mb == 0xffffffffu)) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) mq[i & 3] = fmaxf(mq[i & 3], v[i]);
       } else {
@@ -379,36 +377,49 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // P = exp2(score - max) as bf16 into the K stage, K-major SWIZZLE_128B:
       //   [kv block of 64][row][128 B], 16-byte chunk index ^ (row & 7); my quarter = 4 chunks of block q4 / 2
       unsigned char* prow = smem + TC_TILE_BYTES * (1 + 2 * s) + (q4 >> 1) * TC_HALF_BYTES + row_l * 128;
-      const bool all_vis = (mb == 0xffffffffu);
+      // warp-uniform choice: chunks made of cache columns only (all but the last 1-2 tiles) run a loop with no
+      // mask instructions at all -- the softmax warps are issue-bound, every instruction per element counts
+      const bool all_vis = __all_sync(0xffffffffu, mb == 0xffffffffu);
       float ps4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (all_vis) {
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float p[8];
+        for (int g = 0; g < 4; ++g) {
+          float p[8];
 #pragma unroll
-        for (int e = 0; e < 8; e += 2) {
-          const int i = g * 8 + e;
-          // reference rounding points, two elements per cvt: bf16(bf16(s) * (1/sqrt(d)))
-          float2 r1 = (variant & 2) ? make_float2(v[i], v[i + 1]) : __bfloat1622float2(__floats2bfloat162_rn(v[i], v[i + 1]));
-          float2 r2 = (variant & 1) ? make_float2(r1.x * inv_sqrt_d, r1.y * inv_sqrt_d)
-                                    : __bfloat1622float2(__floats2bfloat162_rn(r1.x * inv_sqrt_d, r1.y * inv_sqrt_d));
-          if (variant & 4) {
-            p[e] = r2.x * TC_LOG2E - off;
-            p[e + 1] = r2.y * TC_LOG2E - off;
-          } else {
+          for (int e = 0; e < 8; e += 2) {
+            const int i = g * 8 + e;
+            // reference rounding points, two elements per cvt: bf16(bf16(s) * (1/sqrt(d)))
+            const float2 r1 = __bfloat1622float2(__floats2bfloat162_rn(v[i], v[i + 1]));
+            const float2 r2 = __bfloat1622float2(__floats2bfloat162_rn(r1.x * inv_sqrt_d, r1.y * inv_sqrt_d));
             p[e] = ex2_approx(r2.x * TC_LOG2E - off);
             p[e + 1] = ex2_approx(r2.y * TC_LOG2E - off);
+            ps4[g] += p[e] + p[e + 1];
           }
-          if (!all_vis) {
-            if (!((mb >> i) & 1u)) p[e] = 0.f;
-            if (!((mb >> (i + 1)) & 1u)) p[e + 1] = 0.f;
-          }
-          ps4[g] += p[e] + p[e + 1];
+          uint4 pk;
+          pk.x = pack2_bf16(p[0], p[1]); pk.y = pack2_bf16(p[2], p[3]);
+          pk.z = pack2_bf16(p[4], p[5]); pk.w = pack2_bf16(p[6], p[7]);
+          const int cc = (q4 & 1) * 4 + g;
+          *reinterpret_cast<uint4*>(prow + ((cc ^ (row_l & 7)) << 4)) = pk;
         }
-        uint4 pk;
-        pk.x = pack2_bf16(p[0], p[1]); pk.y = pack2_bf16(p[2], p[3]);
-        pk.z = pack2_bf16(p[4], p[5]); pk.w = pack2_bf16(p[6], p[7]);
-        const int cc = (q4 & 1) * 4 + g;
-        *reinterpret_cast<uint4*>(prow + ((cc ^ (row_l & 7)) << 4)) = pk;
+      } else {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float p[8];
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            const int i = g * 8 + e;
+            const float2 r1 = __bfloat1622float2(__floats2bfloat162_rn(v[i], v[i + 1]));
+            const float2 r2 = __bfloat1622float2(__floats2bfloat162_rn(r1.x * inv_sqrt_d, r1.y * inv_sqrt_d));
+            p[e] = ((mb >> i) & 1u) ? ex2_approx(r2.x * TC_LOG2E - off) : 0.f;
+            p[e + 1] = ((mb >> (i + 1)) & 1u) ? ex2_approx(r2.y * TC_LOG2E - off) : 0.f;
+            ps4[g] += p[e] + p[e + 1];
+          }
+          uint4 pk;
+          pk.x = pack2_bf16(p[0], p[1]); pk.y = pack2_bf16(p[2], p[3]);
+          pk.z = pack2_bf16(p[4], p[5]); pk.w = pack2_bf16(p[6], p[7]);
+          const int cc = (q4 & 1) * 4 + g;
+          *reinterpret_cast<uint4*>(prow + ((cc ^ (row_l & 7)) << 4)) = pk;
+        }
       }
       l_sum += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
       if (j == 1) TC_STAMP(13, 64);
@@ -557,12 +568,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   cluster_arrive();      // nobody may exit while a sibling still reads its shared memory
   cluster_wait();
   TC_STAMP(TS_END, 0);
-}
-
-int attn_tc_set_variant(int v) {
-  cudaError_t e = cudaMemcpyToSymbol(g_attn_variant, &v, sizeof(v));
-  if (e != cudaSuccess) { set_cuda_error(e, "cudaMemcpyToSymbol(g_attn_variant)"); return LADE_ECUDA; }
-  return LADE_OK;
 }
 
 int attn_tc_set_timing_buffer(void* dev_ptr) {

@@ -10,9 +10,7 @@ from attn_microbench import steady_rowmask
 
 lib = _cabi.load()
 H, D, L = 32, 128, 8
-import itertools
-for (kv, ns), variant in itertools.product([(3072, 4)], [0, 1, 3, 4, 7]):
-    _cabi.check(lib.lade_debug_attn_variant(variant))
+for kv, ns in [(1024, 4), (3072, 4)]:
     rm_np, mw, q_len = steady_rowmask(15, 5, 15)
     cap = kv + q_len + 64
     kvc = torch.randn(L, 2, H, cap, D, device="cuda", dtype=torch.bfloat16)
@@ -38,7 +36,6 @@ for (kv, ns), variant in itertools.product([(3072, 4)], [0, 1, 3, 4, 7]):
     t = t[t[:, 0] > 0]
     names = ["start", "kfull0", "sfull0", "ofinal", "staged", "cluster", "merged", "end", "t1_begin", "t1_sfull", "t1_ld", "t1_max", "t1_bar", "t1_exp", "t1_fence", "t1_arrive"]
     rel = (t - t[:, :1]) / 1.965e3     # us at 1965 MHz
-    print(json.dumps({"variant": variant, "kv": kv, "splits": ns, "ctas": int(len(t)),
+    print(json.dumps({"kv": kv, "splits": ns, "ctas": int(len(t)),
                       "median_us_since_start": {n: round(float(np.median(rel[:, i])), 2) for i, n in enumerate(names)},
                       }))
-_cabi.check(lib.lade_debug_attn_variant(0))
