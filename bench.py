@@ -223,8 +223,18 @@ def attn_roofline(eng, shape, reps=5):
     bytes_alg = 2 * kv_len * Hkv * D * 2 + q_len * Hq * D * 2 + 2 * q_len * Hkv * D * 2 + q_len * Hq * D * 2
     peak, how = measured_peaks()
     achieved = bytes_alg / (us * 1e-6) / 1e9
+    traffic = None            # DRAM bytes per launch from the committed ncu capture closest to this shape
+    try:
+        with open(os.path.join(ROOT, "profiles", "attn_traffic.json")) as f:
+            caps = [c for c in json.load(f)["captures"] if c["q_len"] == q_len]
+        if caps:
+            best = min(caps, key=lambda c: abs(c["kv_len"] - kv_len))
+            if abs(best["kv_len"] - kv_len) <= 64:
+                traffic = best["dram_bytes"]
+    except Exception:
+        traffic = None
     return {"bound": "hbm", "kernel": "lade_attn_fwd", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-            "frac": round(achieved / peak, 4), "traffic": None, "peak_source": how, "us_per_launch": round(us, 2),
+            "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": how, "us_per_launch": round(us, 2),
             "alg_bytes_per_launch": bytes_alg, "kv_len": kv_len, "q_len": q_len, "launches_timed": reps * eng.L}
 
 
