@@ -249,6 +249,11 @@ def cpu_baseline(shape, W, N, G, n_threads, budget_layers=(1, 2), prompt_len=64,
     torch.set_num_threads(n_threads)
     times = {}
     toks = steps = 0
+    # untimed warm-up (oneDNN primitive creation, thread pools) so that the first timed depth is not inflated
+    _w = LR.init_weights(dict(shape, layers=1), seed=0, dtype=torch.bfloat16)
+    _om = LR.OracleLlama(dict(shape, layers=1), _w)
+    LA.greedy_lookahead(list(range(3, 3 + 16)), 2, W, N, G, _om.step_fn, _om.compact_fn, rng=random.Random(0))
+    del _om, _w
     for L in budget_layers:
         cfg = dict(shape, layers=L)
         w = LR.init_weights(cfg, seed=0, dtype=torch.bfloat16)
