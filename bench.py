@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--attn-impl", type=int, default=0)
     ap.add_argument("--attn-splits", type=int, default=0)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--do-sample", action="store_true",
+                    help="BASELINE.json configs[2]: sampling, temperature 0.8, top_k=0, top_p=1.0 (lade/decoding.py:137)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-cuda", action="store_true",
                     help="skip timing the unmodified reference's CUDA-eager loop (needs baseline/_ref)")
@@ -160,11 +162,13 @@ def attn_roofline(eng, shape, reps=5):
     lib = eng.lib
     meta_now = eng.meta.cpu().tolist()
     kv_len = meta_now[_cabi.M_KV_LEN]
-    rows = eng.q_steady
+    # own Q / output buffers at the metric's full shape (under LP the engine's per-rank buffers are smaller)
     # full steady-state layout of the metric's shape (q = (N-1)(W+G) rows: every guess slot filled); random-init
     # weights on a random prompt rarely produce pool hits, so the live decode mostly runs with fewer rows
     W, N, G, GS = eng.W, eng.N, eng.G, eng.GS
     q_len = GS * (W + G)
+    rows = q_len
+    kv_len = min(kv_len, eng.kv_capacity - q_len)          # stay inside the allocated cache rows
     import numpy as np
     vis = np.zeros((q_len, q_len), dtype=bool)            # steady lookahead mask, SURVEY App. B (one GPU)
     for r in range(q_len):
@@ -186,15 +190,17 @@ def attn_roofline(eng, shape, reps=5):
     for k, v in {_cabi.M_Q_LEN: q_len, _cabi.M_KV_LEN: kv_len, _cabi.M_N_INPUT: 1, _cabi.M_TINY: W,
                  _cabi.M_N_LEVELS: N - 1, _cabi.M_N_GUESS_TOK: G * GS, _cabi.M_PHASE: 2, _cabi.M_Q_PAD: rows}.items():
         meta[k] = v
-    qb = eng.qb if rows == eng.rows_cap else eng.qb.view(-1)[: eng.nh * rows * eng.D].view(eng.nh, rows, eng.D)
+    qb = torch.randn(eng.nh, rows, eng.D, device=eng.dev).to(torch.bfloat16)
+    attn_out = torch.empty(rows, eng.nh * eng.D, dtype=torch.bfloat16, device=eng.dev)
+    scratch = torch.zeros(int(lib.lade_attn_scratch_bytes(rows, eng.nh, eng.D, eng.attn_splits)), dtype=torch.uint8, device=eng.dev)
     stream = torch.cuda.current_stream(eng.dev)
 
     def one_pass():
         cs = torch.cuda.current_stream(eng.dev).cuda_stream
         for l in range(eng.L):
             _cabi.check(lib.lade_attn_fwd(cs, qb.data_ptr(), eng.kv[l, 0].data_ptr(), eng.kv[l, 1].data_ptr(),
-                                          eng.attn_out.data_ptr(), rowmask.data_ptr(), mw, meta.data_ptr(),
-                                          eng.attn_scratch.data_ptr(), rows, eng.nh, eng.nkv, eng.D, eng.kv_capacity,
+                                          attn_out.data_ptr(), rowmask.data_ptr(), mw, meta.data_ptr(),
+                                          scratch.data_ptr(), rows, eng.nh, eng.nkv, eng.D, eng.kv_capacity,
                                           eng.kv_capacity, eng.attn_splits, eng.attn_impl))
     for _ in range(3):
         one_pass()
@@ -403,8 +409,22 @@ def main():
         torch.cuda.synchronize()
 
     # ---- warm-up (also captures the steady-step CUDA graph)
+    if args.do_sample:
+        from transformers.generation.logits_process import LogitsProcessorList, TemperatureLogitsWarper
+        from lookaheaddecoding_b200.sampling import sample_lookahead
+        warper = LogitsProcessorList([TemperatureLogitsWarper(0.8)])
+
+        def run_once():
+            torch.manual_seed(2)
+            return sample_lookahead(eng, prompt_list, args.max_new, warper, rng=random.Random(0))
+        gen_kwargs = dict(do_sample=True, temperature=0.8, top_k=0, top_p=1.0)
+        config["workload"] = config["workload"].replace("greedy", "sampling temp=0.8")
+    else:
+        def run_once():
+            return eng.generate(prompt_list, args.max_new, rng=random.Random(0))
+        gen_kwargs = dict(do_sample=False)
     for _ in range(max(args.warmup, 1)):
-        eng.generate(prompt_list, args.max_new, rng=random.Random(0))
+        run_once()
     barrier()
 
     # ---- device-timed: prompt already with the engine
@@ -418,7 +438,7 @@ def main():
             torch.cuda.profiler.start()
         e0.record()
         for _ in range(args.steps):
-            out = eng.generate(prompt_list, args.max_new, rng=random.Random(0))
+            out = run_once()
             toks += len(out) - P
             steps += eng.last_steps
         e1.record()
@@ -434,7 +454,9 @@ def main():
         for _ in range(args.steps):
             random.seed(0)
             ids = prompt_host.to(dev, non_blocking=True)
-            o = model.generate(ids, attention_mask=torch.ones_like(ids), max_new_tokens=args.max_new, do_sample=False)
+            if args.do_sample:
+                torch.manual_seed(2)
+            o = model.generate(ids, attention_mask=torch.ones_like(ids), max_new_tokens=args.max_new, **gen_kwargs)
             o_host = o.cpu()
             e2e_toks += o_host.shape[1] - P
         barrier()
