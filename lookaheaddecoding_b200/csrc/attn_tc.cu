@@ -499,68 +499,84 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int row_lo = split * per;
     const int n_rows = max(0, min(TC_BM, row_lo + per) - row_lo);
     const uint32_t sml_a = sQ_a + TC_SML_OFFSET, so_a = sQ_a + TC_SO_OFFSET;
-    // item = (row, 8 columns).  A thread issues the loads of an item together -- (m, l) of every split and the two
-    // float4 of the first four splits, all independent -- so the DSMEM latency is paid once per item.
-    const int n_items = n_rows * (TC_D / 8);
-    for (int idx = threadIdx.x; idx < n_items; idx += TC_THREADS) {
-      const int r = idx / (TC_D / 8), c8 = idx % (TC_D / 8);
-      const uint32_t ml_a = sml_a + (uint32_t)(row_lo + r) * 8u;
-      const uint32_t o_a = so_a + (uint32_t)((row_lo + r) * TC_SO_STRIDE + c8 * 8) * 4u;
-      float2 ml[8];
-      float4 va[4], vb[4];
+    // item = (row, 4 columns): consecutive lanes read consecutive float4 of one staged row (conflict-free in the
+    // sibling's shared memory, one 512-byte row per warp instruction).
+    const int n_items = n_rows * (TC_D / 4);
+    if (n_active <= 4) {
+      // common case: a thread issues every load of its (up to 3) items before using any of them
+      for (int base = 0; base < n_items; base += 3 * TC_THREADS) {
+        float2 ml[3][4];
+        float4 v[3][4];
 #pragma unroll
-      for (int sp = 0; sp < 8; ++sp) ml[sp] = sp < n_active ? ld_dsmem_f2(dsmem_addr(ml_a, sp)) : make_float2(-INFINITY, 0.f);
+        for (int k = 0; k < 3; ++k) {
+          const int idx = base + k * TC_THREADS + threadIdx.x;
+          const bool ok = idx < n_items;
+          const int r = ok ? idx / (TC_D / 4) : 0, c4 = idx % (TC_D / 4);
+          const uint32_t ml_a = sml_a + (uint32_t)(row_lo + r) * 8u;
+          const uint32_t o_a = so_a + (uint32_t)((row_lo + r) * TC_SO_STRIDE + c4 * 4) * 4u;
 #pragma unroll
-      for (int sp = 0; sp < 4; ++sp) {
-        if (sp < n_active) {
-          const uint32_t ra = dsmem_addr(o_a, sp);
-          va[sp] = ld_dsmem_f4(ra);
-          vb[sp] = ld_dsmem_f4(ra + 16);
-        } else {
-          va[sp] = make_float4(0.f, 0.f, 0.f, 0.f);
-          vb[sp] = va[sp];
-        }
-      }
-      float mmax = -INFINITY;
-#pragma unroll
-      for (int sp = 0; sp < 8; ++sp) mmax = fmaxf(mmax, ml[sp].x);
-      float wv[8], lsum = 0.f;
-#pragma unroll
-      for (int sp = 0; sp < 8; ++sp) {
-        wv[sp] = (ml[sp].x == -INFINITY) ? 0.f : exp2f((ml[sp].x - mmax) * TC_LOG2E);
-        lsum += ml[sp].y * wv[sp];
-      }
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-#pragma unroll
-      for (int sp = 0; sp < 4; ++sp) {
-        a.x += va[sp].x * wv[sp]; a.y += va[sp].y * wv[sp]; a.z += va[sp].z * wv[sp]; a.w += va[sp].w * wv[sp];
-        b.x += vb[sp].x * wv[sp]; b.y += vb[sp].y * wv[sp]; b.z += vb[sp].z * wv[sp]; b.w += vb[sp].w * wv[sp];
-      }
-      if (n_active > 4) {
-#pragma unroll
-        for (int sp = 4; sp < 8; ++sp) {
-          if (sp < n_active) {
-            const uint32_t ra = dsmem_addr(o_a, sp);
-            va[sp - 4] = ld_dsmem_f4(ra);
-            vb[sp - 4] = ld_dsmem_f4(ra + 16);
-          } else {
-            va[sp - 4] = make_float4(0.f, 0.f, 0.f, 0.f);
-            vb[sp - 4] = va[sp - 4];
+          for (int sp = 0; sp < 4; ++sp) {
+            const bool live = ok && sp < n_active;
+            ml[k][sp] = live ? ld_dsmem_f2(dsmem_addr(ml_a, sp)) : make_float2(-INFINITY, 0.f);
+            v[k][sp] = live ? ld_dsmem_f4(dsmem_addr(o_a, sp)) : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
 #pragma unroll
-        for (int sp = 4; sp < 8; ++sp) {
-          a.x += va[sp - 4].x * wv[sp]; a.y += va[sp - 4].y * wv[sp]; a.z += va[sp - 4].z * wv[sp]; a.w += va[sp - 4].w * wv[sp];
-          b.x += vb[sp - 4].x * wv[sp]; b.y += vb[sp - 4].y * wv[sp]; b.z += vb[sp - 4].z * wv[sp]; b.w += vb[sp - 4].w * wv[sp];
+        for (int k = 0; k < 3; ++k) {
+          const int idx = base + k * TC_THREADS + threadIdx.x;
+          if (idx >= n_items) continue;
+          const int r = idx / (TC_D / 4), c4 = idx % (TC_D / 4);
+          const float mmax = fmaxf(fmaxf(ml[k][0].x, ml[k][1].x), fmaxf(ml[k][2].x, ml[k][3].x));
+          float lsum = 0.f;
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int sp = 0; sp < 4; ++sp) {
+            const float wgt = (ml[k][sp].x == -INFINITY) ? 0.f : exp2f((ml[k][sp].x - mmax) * TC_LOG2E);
+            lsum += ml[k][sp].y * wgt;
+            a.x += v[k][sp].x * wgt; a.y += v[k][sp].y * wgt; a.z += v[k][sp].z * wgt; a.w += v[k][sp].w * wgt;
+          }
+          const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
+          const int row = mt * TC_BM + row_lo + r;
+          if (row < q_pad) {
+            uint2 pk;
+            pk.x = pack2_bf16(a.x * inv, a.y * inv);
+            pk.y = pack2_bf16(a.z * inv, a.w * inv);
+            *reinterpret_cast<uint2*>(out + (long long)row * HD + h * TC_D + c4 * 4) = pk;
+          }
         }
       }
-      const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
-      const int row = mt * TC_BM + row_lo + r;
-      if (row < q_pad) {
-        uint4 pk;
-        pk.x = pack2_bf16(a.x * inv, a.y * inv); pk.y = pack2_bf16(a.z * inv, a.w * inv);
-        pk.z = pack2_bf16(b.x * inv, b.y * inv); pk.w = pack2_bf16(b.z * inv, b.w * inv);
-        *reinterpret_cast<uint4*>(out + (long long)row * HD + h * TC_D + c8 * 8) = pk;
+    } else {
+      for (int idx = threadIdx.x; idx < n_items; idx += TC_THREADS) {
+        const int r = idx / (TC_D / 4), c4 = idx % (TC_D / 4);
+        const uint32_t ml_a = sml_a + (uint32_t)(row_lo + r) * 8u;
+        const uint32_t o_a = so_a + (uint32_t)((row_lo + r) * TC_SO_STRIDE + c4 * 4) * 4u;
+        float2 ml[8];
+        float4 v[8];
+#pragma unroll
+        for (int sp = 0; sp < 8; ++sp) {
+          const bool live = sp < n_active;
+          ml[sp] = live ? ld_dsmem_f2(dsmem_addr(ml_a, sp)) : make_float2(-INFINITY, 0.f);
+          v[sp] = live ? ld_dsmem_f4(dsmem_addr(o_a, sp)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float mmax = -INFINITY;
+#pragma unroll
+        for (int sp = 0; sp < 8; ++sp) mmax = fmaxf(mmax, ml[sp].x);
+        float lsum = 0.f;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int sp = 0; sp < 8; ++sp) {
+          const float wgt = (ml[sp].x == -INFINITY) ? 0.f : exp2f((ml[sp].x - mmax) * TC_LOG2E);
+          lsum += ml[sp].y * wgt;
+          a.x += v[sp].x * wgt; a.y += v[sp].y * wgt; a.z += v[sp].z * wgt; a.w += v[sp].w * wgt;
+        }
+        const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
+        const int row = mt * TC_BM + row_lo + r;
+        if (row < q_pad) {
+          uint2 pk;
+          pk.x = pack2_bf16(a.x * inv, a.y * inv);
+          pk.y = pack2_bf16(a.z * inv, a.w * inv);
+          *reinterpret_cast<uint2*>(out + (long long)row * HD + h * TC_D + c4 * 4) = pk;
+        }
       }
     }
   }
