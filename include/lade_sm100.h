@@ -167,6 +167,20 @@ int64_t lade_attn_scratch_bytes(int32_t q_pad, int32_t n_heads, int32_t head_dim
  * siblings arrived, merged, end). */
 int lade_debug_attn_timing(void* dev_buffer);
 
+/* Projection GEMM of the lookahead step: c[m][n] (row stride ldc) = a[m][k] . w[n][k]^T, bf16 in/out, fp32
+ * accumulation on tcgen05 tensor cores; w is an nn.Linear weight ([out_features][in_features], row-major).
+ * Replaces q/k/v_proj (modeling_llama.py:447-449), o_proj (:541), gate/up/down_proj (:378) and lm_head (:1608)
+ * for step row counts m <= 128; `a_rows` >= m is the number of addressable rows of the `a` buffer (rows >= m
+ * are read but never stored).  tile_n / split_k = 0 lets the library pick (one wave of CTAs over the SMs);
+ * tuning knobs ride in tile_n: bits [16,20) = pipeline depth cap, bit 20 = do not prefill the ring during CTA set-up.
+ * Returns LADE_EUNSUPPORTED for m > 128, k % 64 != 0 or n % 8 != 0 (callers then use a library GEMM). */
+int lade_gemm_bf16(void* stream, const void* a, const void* w, void* c, int32_t m, int32_t a_rows, int32_t n, int32_t k,
+                   int32_t ldc, int32_t tile_n, int32_t split_k);
+
+/* Profiling aid: when set (device buffer of 4 * 1024 * 8 int64, or NULL to disable) the GEMM kernel records
+ * %globaltimer (ns) at its phase boundaries per CTA, the last 4 launches round-robin. */
+int lade_debug_gemm_timing(void* dev_buffer);
+
 /* act = bf16(silu(gate)) * up on the fused [rows][2*inter] projection.  LlamaMLP, modeling_llama.py:378. */
 int lade_swiglu(void* stream, const void* gate_up, void* out, int32_t rows, int32_t inter);
 

@@ -19,6 +19,7 @@ META_INTS = 16
 R_N_EMIT, R_MAX_HIT, R_MAX_HIT_IDX, R_KV_SRC, R_KV_DST, R_KV_LEN, R_DONE, R_N_OUT, R_STEPS, R_N_GUESS = range(10)
 R_HITS = 16
 RES_INTS = 48
+LADE_OK, LADE_EINVAL, LADE_ECUDA, LADE_ENOMEM, LADE_EUNSUPPORTED, LADE_ESTATE = 0, -1, -2, -3, -4, -5
 ROW_PREFIX, ROW_WINDOW, ROW_GUESS, ROW_PAD = 0, 1, 2, 3
 
 
@@ -46,6 +47,8 @@ _SIGNATURES = {
     "lade_attn_fwd": (C.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_p, c_p] + [c_i32] * 8),
     "lade_attn_scratch_bytes": (C.c_int64, [c_i32, c_i32, c_i32, c_i32]),
     "lade_debug_attn_timing": (C.c_int, [c_p]),
+    "lade_gemm_bf16": (C.c_int, [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32]),
+    "lade_debug_gemm_timing": (C.c_int, [c_p]),
     "lade_swiglu": (C.c_int, [c_p, c_p, c_p, c_i32, c_i32]),
     "lade_argmax_rows": (C.c_int, [c_p, c_p, c_i32, c_i32, c_i32, c_p]),
     "lade_accept_update": (C.c_int, [c_p, c_p, c_p, c_p, c_p]),
