@@ -30,6 +30,7 @@ LP_CASES = [
     ("lp3_fp32_w7n4g6", "float32", 7, 4, 6, True, 3, 32, 64, 0, 9),
     ("lp4_fp32_w5n3g3_pool", "float32", 5, 3, 3, True, 4, 24, 48, 0, 1),
     ("lp2_bf16_w15n5g15_pool", "bfloat16", 15, 5, 15, True, 2, 64, 96, 1, 4),
+    ("lp8_fp32_w15n5g15_pool", "float32", 15, 5, 15, True, 8, 40, 64, 0, 6),
 ]
 
 
