@@ -244,16 +244,43 @@ def attn_roofline(eng, shape, reps=5):
             "alg_bytes_per_launch": bytes_alg, "kv_len": kv_len, "q_len": q_len, "launches_timed": reps * eng.L}
 
 
-def cpu_baseline(shape, W, N, G, n_threads, budget_layers=(1, 2), prompt_len=64, max_new=12):
+def usable_cores() -> int:
+    """Host cores this process may really use: affinity mask, clipped by the cgroup CPU quota (os.cpu_count() reports
+    the machine, and oversubscribing a quota-limited container makes the CPU baseline slow and erratic)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except (OSError, ValueError):
+        try:    # cgroup v1
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as f:
+                quota = int(f.read())
+            with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+                period = int(f.read())
+            if quota > 0 and period > 0:
+                n = max(1, min(n, quota // period))
+        except (OSError, ValueError):
+            pass
+    return n
+
+
+def cpu_baseline(shape, W, N, G, n_threads, budget_layers=(1, 3), prompt_len=64, max_new=12):
     """Oracle port of the reference loop (oracle/, reference eager numerics) on the host cores, on a bounded
-    sample: full widths, `budget_layers` decoder layers, short prompt; per-step time is extrapolated
-    linearly in depth to the full layer count (t = a + b*L fitted on the two depths)."""
+    sample: full widths, `budget_layers` decoder layers, short prompt.  Every forward step is timed on its own and
+    the MEDIAN steady step per depth is used (128 host threads are noisy); the per-layer cost is the difference of
+    the two depths and the full-depth step is extrapolated linearly (t = t[l1] + per_layer * (L - l1))."""
+    import statistics
     import torch
     from oracle import llama_ref as LR
     from oracle import lookahead as LA
 
     torch.set_num_threads(n_threads)
-    times = {}
+    med = {}
     toks = steps = 0
     # untimed warm-up (oneDNN primitive creation, thread pools) so that the first timed depth is not inflated
     _w = LR.init_weights(dict(shape, layers=1), seed=0, dtype=torch.bfloat16)
@@ -266,19 +293,31 @@ def cpu_baseline(shape, W, N, G, n_threads, budget_layers=(1, 2), prompt_len=64,
         om = LR.OracleLlama(cfg, w)
         g = torch.Generator().manual_seed(1)
         prompt = torch.randint(3, shape["vocab"], (prompt_len,), generator=g).tolist()
-        t0 = time.time()
-        out, st = LA.greedy_lookahead(prompt, max_new, W, N, G, om.step_fn, om.compact_fn, rng=random.Random(0))
-        times[L] = (time.time() - t0) / st
+        durations = []
+
+        def timed_step(*a, _f=om.step_fn, **k):
+            t0 = time.perf_counter()
+            r = _f(*a, **k)
+            durations.append(time.perf_counter() - t0)
+            return r
+
+        out, st = LA.greedy_lookahead(prompt, max_new, W, N, G, timed_step, om.compact_fn, rng=random.Random(0))
+        steady = durations[N - 1:] if len(durations) > N + 1 else durations     # drop prefill + window-fill steps
+        med[L] = statistics.median(steady)
         toks, steps = len(out) - prompt_len, st
         del om, w
     (l1, l2) = budget_layers
-    b = (times[l2] - times[l1]) / (l2 - l1)
-    a = times[l1] - b * l1
-    t_full = a + b * shape["layers"]
-    return {"value": round((toks / steps) / t_full, 3), "unit": "tokens/s", "cores": n_threads, "kind": "port",
+    per_layer = (med[l2] - med[l1]) / (l2 - l1)
+    note = ""
+    if per_layer <= 0:                      # noise larger than the signal: fall back to an upper bound per layer
+        per_layer = med[l2] / l2
+        note = " (depth difference non-positive: per-layer cost taken as t/L of the deeper sample)"
+    t_full = med[l1] + per_layer * (shape["layers"] - l1)
+    return {"value": round((toks / steps) / t_full, 4), "unit": "tokens/s", "cores": n_threads, "kind": "port",
             "sample": f"oracle port (reference eager numerics) on CPU: full widths, {l1} and {l2} of {shape['layers']} layers, "
-                      f"P={prompt_len}, {max_new} new tokens ({steps} steps); per-step time extrapolated linearly in depth "
-                      f"({times[l1]:.2f}s@{l1}L, {times[l2]:.2f}s@{l2}L -> {t_full:.2f}s/step), {toks / steps:.2f} tokens/step"}
+                      f"P={prompt_len}, {max_new} new tokens ({steps} steps); median steady forward step "
+                      f"{med[l1]:.3f}s@{l1}L, {med[l2]:.3f}s@{l2}L -> {per_layer:.3f}s/layer -> {t_full:.2f}s/step{note}, "
+                      f"{toks / steps:.2f} tokens/step"}
 
 
 def reference_cuda_eager(shape, W, N, G, P, max_new, device):
@@ -362,7 +401,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        n_threads = os.cpu_count() or 1
+        n_threads = usable_cores()
         cb = cpu_baseline(shape, W, N, G, n_threads)
         line = {"metric": metric, "value": cb["value"], "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
@@ -478,11 +517,11 @@ def main():
             ref_cuda = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
     clocks = sampler.summary()
     cb = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # host-core baseline: rank 0 at N=1 only
         try:
-            cb = cpu_baseline(shape, W, N, G, os.cpu_count() or 1)
+            cb = cpu_baseline(shape, W, N, G, usable_cores())
         except Exception as ex:  # the baseline is reporting only; never hide the GPU numbers
-            cb = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+            cb = {"value": None, "unit": "tokens/s", "cores": usable_cores(), "kind": "port", "sample": f"failed: {ex}"}
     value = toks / (dev_ms * 1e-3)
     line = {
         "metric": metric, "value": round(value, 2), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,

@@ -36,7 +36,7 @@ def _source_hash() -> str:
     files.append(os.path.join(os.path.dirname(PKG_DIR), "include", "lade_sm100.h"))
     for f in files:
         with open(f, "rb") as fh:
-            h.update(f.encode())
+            h.update(os.path.basename(f).encode())     # names, not absolute paths: the tree is relocatable
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
@@ -54,15 +54,32 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and is_fresh():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
-    with open(STAMP, "w") as f:
-        f.write(_source_hash())
+    # Several ranks may get here at once (torchrun): serialise on a lock file, re-check under the lock, and publish the
+    # library with an atomic rename so no process can ever dlopen a half-written file.
+    import fcntl
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_fresh():
+                return LIB_PATH
+            tmp = LIB_PATH + f".tmp.{os.getpid()}"
+            cmd = [_find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+                  ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            if verbose:
+                print(res.stderr)
+            if os.path.exists(STAMP):
+                os.remove(STAMP)
+            os.replace(tmp, LIB_PATH)
+            with open(STAMP + ".tmp", "w") as f:
+                f.write(_source_hash())
+            os.replace(STAMP + ".tmp", STAMP)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
