@@ -54,7 +54,7 @@ SHAPES = [
     (120, 12288, 4096, 192 | (3 << 16), 2),
     (120, 22016, 4096, 160 | (1 << 20), 1),
     (76, 32000, 4096, 224 | (2 << 16) | (1 << 20), 1),
-    (120, 4096, 11008, 128 | (1 << 16), 4),
+    (120, 4096, 11008, 128 | (3 << 16), 4),
 ]
 
 
