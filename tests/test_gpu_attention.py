@@ -16,7 +16,7 @@ from oracle import lookahead as LA
 
 pytestmark = pytest.mark.gpu
 ATOL_MAX, ATOL_MEAN = 2e-2, 2e-3
-IMPLS = [int(x) for x in os.environ.get("LADE_TEST_ATTN_IMPLS", "1").split(",")]
+IMPLS = [int(x) for x in os.environ.get("LADE_TEST_ATTN_IMPLS", "2,1").split(",")]   # 2 = tcgen05 (product default), 1 = mma.sync fallback
 
 
 def run_kernel(q, k, v, lay, meta_vals, q_pad, n_splits, impl, kv_capacity=None):
