@@ -52,8 +52,9 @@ class LookaheadEngine:
     def __init__(self, model, window_size: int, level: int, guess_set_size: int,
                  pool_from_prompt: bool = False, max_total_len: int = 4096, attn_impl: int = 0,
                  attn_splits: Optional[int] = None, use_cuda_graph: bool = True, debug: bool = False,
-                 dist_workers: int = 1, rank: int = 0, process_group=None):
+                 dist_workers: int = 1, rank: int = 0, process_group=None, pipeline_host: bool = True):
         self.lib = _cabi.load()
+        self.pipeline_host = bool(pipeline_host)
         cfg = model.config
         p0 = next(model.parameters())
         if p0.device.type != "cuda":
@@ -115,6 +116,9 @@ class LookaheadEngine:
         self._lcfg = None
         self._graph = None
         self._pinned_res = torch.empty(_cabi.RES_INTS, dtype=torch.int32, pin_memory=True)
+        # two result slots + events: the host reads step i's record while step i+1 is already queued on the GPU
+        self._pinned_ring = [torch.empty(_cabi.RES_INTS, dtype=torch.int32, pin_memory=True) for _ in range(2)]
+        self._res_events = [torch.cuda.Event() for _ in range(2)]
         self.launches = 0   # kernels of THIS repo launched (graph replays counted by their content)
         self._launches_per_graph = 0
         self.last_steps = 0
@@ -295,14 +299,26 @@ class LookaheadEngine:
         check(lib.lade_lp_commit(self._ctx, stream, _ptr(self.lp_recv), _ptr(self.meta), _ptr(self.res)), "lade_lp_commit")
         return 1
 
-    def _read_result(self) -> StepRecord:
-        self._pinned_res.copy_(self.res, non_blocking=True)
-        torch.cuda.current_stream(self.dev).synchronize()
-        r = self._pinned_res.numpy()
+    @staticmethod
+    def _parse_result(r) -> StepRecord:
         n_emit = int(r[_cabi.R_N_EMIT])
         return StepRecord(n_emit=n_emit, max_hit=int(r[_cabi.R_MAX_HIT]),
                           hits=[int(x) for x in r[_cabi.R_HITS:_cabi.R_HITS + n_emit]],
                           n_guess=int(r[_cabi.R_N_GUESS]), kv_len=int(r[_cabi.R_KV_LEN]), done=bool(r[_cabi.R_DONE]))
+
+    def _read_result(self) -> StepRecord:
+        self._pinned_res.copy_(self.res, non_blocking=True)
+        torch.cuda.current_stream(self.dev).synchronize()
+        return self._parse_result(self._pinned_res.numpy())
+
+    def _enqueue_result_copy(self, slot: int) -> None:
+        """Stream-ordered D2H copy of the step record into pinned slot `slot`, marked by an event."""
+        self._pinned_ring[slot].copy_(self.res, non_blocking=True)
+        self._res_events[slot].record(torch.cuda.current_stream(self.dev))
+
+    def _wait_result(self, slot: int) -> StepRecord:
+        self._res_events[slot].synchronize()
+        return self._parse_result(self._pinned_ring[slot].numpy())
 
     def _steady_graph(self, commit: bool = True):
         if self._graph is None:
@@ -376,18 +392,43 @@ class LookaheadEngine:
         stream = torch.cuda.current_stream(self.dev).cuda_stream
         out = list(prompt)
         self.last_records = []
-        step = 0
-        done = False
-        while not done:
-            self.run_forward_step(step, P)
+        # The decode state lives on the device, so step i+1 never needs the host's view of step i: it is queued
+        # while the host is still waiting for step i's record (the 48-int D2H copy), which hides the host
+        # turn-around (~60 us per step).  Step i+1 is NOT queued when step i certainly ends the generation
+        # (every step emits >= 1 token); if the end comes early (EOS, multi-token accept) the one surplus step runs
+        # on a finished state, where the commit kernels are no-ops, and its record is dropped.
+        inflight: List[int] = []      # result slots of queued steps, oldest first
+        queued = 0                    # steps queued so far
+        step = 0                      # steps whose record has been read
+        guard = max_new_tokens + self.N + 4
+
+        def enqueue():
+            nonlocal queued
+            self.run_forward_step(queued, P)
             if self.DW > 1:
                 self.launches += self._launch_commit(stream)
-            rec = self._read_result()
+            slot = queued & 1
+            self._enqueue_result_copy(slot)
+            inflight.append(slot)
+            queued += 1
+
+        enqueue()
+        while True:
+            certainly_last = (len(out) - P) + 1 >= max_new_tokens
+            if self.pipeline_host and len(inflight) == 1 and not certainly_last:
+                enqueue()
+            rec = self._wait_result(inflight.pop(0))
             self.last_records.append(rec)
             out.extend(rec.hits)
-            done = rec.done
             step += 1
-            if step > max_new_tokens + self.N + 4:
+            if rec.done:
+                break
+            if step > guard:
                 raise LadeError("decode loop did not terminate (device state corrupt?)")
+            if not inflight:
+                enqueue()
+        if inflight:                  # surplus speculative step: let it drain, ignore its record
+            torch.cuda.current_stream(self.dev).synchronize()
+            inflight.clear()
         self.last_steps = step
         return out[:max_length]                                   # lade/decoding.py:1221-1225

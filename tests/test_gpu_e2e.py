@@ -116,6 +116,33 @@ def test_eos_stops_generation():
     eng.close()
 
 
+@pytest.mark.parametrize("name", ["tiny_bf16_w15n5g15_pool", "tiny_bf16_w5n3g3"])
+def test_pipelined_host_loop_is_transparent(name):
+    """Queueing step i+1 before step i's record is read must not change ids, step count or the per-step records --
+    including an early stop on EOS, where one surplus step runs on the finished device state and is dropped."""
+    from lookaheaddecoding_b200 import LookaheadEngine
+    c = CASES[name]
+    model, _ = build_hf_llama(c["model"], c["weight_seed"])
+    P = len(c["prompt"])
+    runs = {}
+    for pipe in (False, True):
+        eng = LookaheadEngine(model, c["W"], c["N"], c["G"], pool_from_prompt=c["pool_from_prompt"],
+                              max_total_len=P + 64, pipeline_host=pipe)
+        full = eng.generate(c["prompt"], 64, rng=random.Random(3))
+        rec_full = [(r.n_emit, r.max_hit, tuple(r.hits), r.kv_len, r.done) for r in eng.last_records]
+        eos = full[P + 17]
+        cut = eng.generate(c["prompt"], 64, eos_token_ids=[eos], rng=random.Random(3))
+        steps_cut = eng.last_steps
+        again = eng.generate(c["prompt"], 64, rng=random.Random(3))       # state after a surplus step is clean
+        short = eng.generate(c["prompt"], 1, rng=random.Random(3))
+        eng.close()
+        runs[pipe] = (full, rec_full, cut, steps_cut, again, short)
+    assert runs[True] == runs[False]
+    full, _, cut, _, again, short = runs[True]
+    assert again == full and short == full[: P + 1]
+    assert cut == full[: len(cut)] and len(cut) < len(full)
+
+
 def test_unsupported_inputs_fail_loudly():
     from lookaheaddecoding_b200 import LookaheadEngine, LadeError
     from lookaheaddecoding_b200.decoding import jacobi_greedy_search_multilevel
