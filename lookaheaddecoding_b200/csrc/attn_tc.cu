@@ -14,6 +14,7 @@
 // same register predicate (common.cuh row_sees == modeling_llama.py:115-207).
 #include "tc_common.cuh"
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -96,12 +97,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int b = 0; b < 2; ++b) { mbar_init(BAR(B_SFULL + b), 1); mbar_init(BAR(B_PFULL + b), TC_SOFTMAX_THREADS / 32); }
       mbar_init(BAR(B_OFINAL), 1);
       fence_barrier_init();
-      // start the memory stream before anything else: Q and the first STAGES K/V tiles are in flight while the
-      // other warps allocate TMEM and meet at the barrier below
-      mbar_expect_tx(BAR(B_QFULL), TC_TILE_BYTES);
-      tma_load_3d(sQ_a, &tmQ, BAR(B_QFULL), 0, mt * TC_BM, h);
-      tma_load_3d(sQ_a + TC_HALF_BYTES, &tmQ, BAR(B_QFULL), 64, mt * TC_BM, h);
-      for (int j = 0; j < my_tiles && j < TC_STAGES; ++j) {
+      // Start the memory stream before anything else, while the other warps allocate TMEM and meet at the barrier
+      // below.  With programmatic dependent launch this CTA may already be running while the producer of this
+      // step's Q and new K/V rows (lade_rope_append) is still in flight: cache tiles entirely below kv_len were
+      // written by earlier steps and are fetched at once; Q and tiles touching rows >= kv_len wait for the producer.
+      auto issue_tile = [&](int j) {
         const int row0 = (tile_lo + j) * TC_BN;
         mbar_expect_tx(BAR(B_KFULL + j), TC_TILE_BYTES);
         tma_load_3d(sK_a(j), &tmK, BAR(B_KFULL + j), 0, row0, hk);
@@ -109,7 +109,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_expect_tx(BAR(B_VFULL + j), TC_TILE_BYTES);
         tma_load_3d(sV_a(j), &tmV, BAR(B_VFULL + j), 0, row0, hk);
         tma_load_3d(sV_a(j) + TC_HALF_BYTES, &tmV, BAR(B_VFULL + j), 64, row0, hk);
-      }
+      };
+      const int n_pre = my_tiles < TC_STAGES ? my_tiles : TC_STAGES;
+      int n_old = 0;                                   // leading tiles that hold only rows of earlier steps
+      while (n_old < n_pre && (tile_lo + n_old + 1) * TC_BN <= kv_len) ++n_old;
+      for (int j = 0; j < n_old; ++j) issue_tile(j);
+      griddep_wait();
+      mbar_expect_tx(BAR(B_QFULL), TC_TILE_BYTES);
+      tma_load_3d(sQ_a, &tmQ, BAR(B_QFULL), 0, mt * TC_BM, h);
+      tma_load_3d(sQ_a + TC_HALF_BYTES, &tmQ, BAR(B_QFULL), 64, mt * TC_BM, h);
+      for (int j = n_old; j < n_pre; ++j) issue_tile(j);
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
     tc_fence_before();
@@ -514,6 +523,15 @@ static int get_tensor_map(const void* ptr, int rows, int heads, CUtensorMap* out
   return LADE_OK;
 }
 
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LADE_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 int attn_fwd_tc_launch(cudaStream_t stream, const void* q, const void* k_cache, const void* v_cache, void* out,
                        const uint32_t* rowmask, int mask_words, const int32_t* meta, void* scratch, int q_pad, int n_heads,
                        int n_kv_heads, int head_dim, int kv_capacity, int kv_bound, int n_splits) {
@@ -540,13 +558,17 @@ int attn_fwd_tc_launch(cudaStream_t stream, const void* q, const void* k_cache, 
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = TC_SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;   // the splits of one (head, q tile) form a cluster
   attr[0].val.clusterDim.x = n_splits;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  // programmatic dependent launch: the grid may start while its stream predecessor (lade_rope_append, which signals
+  // griddepcontrol.launch_dependents at entry) is still running; the kernel orders itself with griddepcontrol.wait
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   const float inv_sqrt_d = 1.0f / sqrtf((float)head_dim);
   cudaError_t e = cudaLaunchKernelEx(&cfg, attn_fwd_tc_kernel, tmQ, tmK, tmV, (__nv_bfloat16*)out, rowmask, mask_words, meta,
                                      q_pad, n_heads, n_kv_heads, n_splits, inv_sqrt_d);

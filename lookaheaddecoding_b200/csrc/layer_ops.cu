@@ -81,6 +81,9 @@ __global__ void __launch_bounds__(256) rope_append_kernel(
     const __nv_bfloat16* __restrict__ sin_tab, const int* __restrict__ pos, const int* __restrict__ meta,
     __nv_bfloat16* __restrict__ q_out, __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache,
     int q_pad, int n_heads, int n_kv_heads, int D, int kv_capacity, int max_pos) {
+  // programmatic dependent launch: let the consumer (lade_attn_fwd) start its prologue and prefetch the cache tiles of
+  // earlier steps while this grid runs; it orders itself with griddepcontrol.wait before touching what is written here
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int r = blockIdx.x;
   const int half = D >> 1;
   const int per_head = half >> 3;                        // 16-byte slices per half head
