@@ -1,0 +1,133 @@
+"""Host-side mirror of the reference's plugin surface (lade/utils.py, lade/decoding.py proxies): CPU-only checks.
+
+No compute is launched; these tests cover configuration plumbing, the reversible generate() patch, the loud
+failures the drop-in promises (no CPU fallback, no silent oracle path) and small host helpers."""
+import io
+import os
+import re
+import contextlib
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the product packages may import it."""
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b|from\s+\.\.?oracle\b)", re.M)
+    for pkg in ("lookaheaddecoding_b200", "lade"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, pkg)):
+            for f in files:
+                if f.endswith(".py"):
+                    src = open(os.path.join(dirpath, f)).read()
+                    assert not pat.search(src), f"{pkg}/{f} imports oracle"
+                    assert "/root/reference" not in src, f"{pkg}/{f} reads the reference checkout"
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from lookaheaddecoding_b200 import _cabi, build
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(build, "LIB_PATH", str(tmp_path / "liblade_sm100.so"))
+    monkeypatch.setattr(build, "is_fresh", lambda: False)
+
+    def no_nvcc(*a, **k):
+        raise RuntimeError("nvcc not found")
+
+    monkeypatch.setattr(build, "build", no_nvcc)
+    with pytest.raises(_cabi.LadeError, match="missing and could not be built"):
+        _cabi.load()
+    with pytest.raises(_cabi.LadeError, match="no CPU fallback"):
+        _cabi.load(build_if_missing=False)
+
+
+def test_cpu_model_is_rejected_not_emulated():
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from lookaheaddecoding_b200 import LookaheadEngine, LadeError
+    cfg = LlamaConfig(hidden_size=256, num_hidden_layers=1, num_attention_heads=2, num_key_value_heads=2,
+                      intermediate_size=688, vocab_size=512, max_position_embeddings=256)
+    model = LlamaForCausalLM(cfg).to(torch.bfloat16)
+    with pytest.raises(LadeError):
+        LookaheadEngine(model, 5, 3, 3)
+
+
+def test_config_lade_populates_config_map_like_the_reference():
+    import lade
+    from lookaheaddecoding_b200.decoding import CONFIG_MAP
+    CONFIG_MAP.clear()
+    lade.config_lade(LEVEL=7, WINDOW_SIZE=20, GUESS_SET_SIZE=20, DEBUG=1, POOL_FROM_PROMPT=True, USE_FLASH=True,
+                     ALWAYS_FWD_ONE=1, SPLIT_FLAG=0)
+    assert CONFIG_MAP["LEVEL"] == 7 and CONFIG_MAP["WINDOW_SIZE"] == 20 and CONFIG_MAP["GUESS_SET_SIZE"] == 20
+    assert CONFIG_MAP["POOL_FROM_PROMPT"] is True and CONFIG_MAP["USE_FLASH"] is True and CONFIG_MAP["log"] == []
+    assert "DIST_WORKERS" not in CONFIG_MAP                      # only set for > 1 workers (lade/utils.py:28)
+    CONFIG_MAP["log"] = [(10, 4), (6, 4)]
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        lade.log_history()
+    assert "OVERALL GEN:  16" in buf.getvalue() and "STEPS:  8" in buf.getvalue() and "2.0" in buf.getvalue()
+    with contextlib.redirect_stdout(io.StringIO()):
+        lade.log_history(clear=True)
+    assert CONFIG_MAP["log"] == []
+
+
+def test_save_log_round_trip(tmp_path):
+    import lade
+    from lookaheaddecoding_b200.decoding import CONFIG_MAP
+    CONFIG_MAP["log"] = [(5, 2)]
+    path = str(tmp_path / "log.pt")
+    lade.save_log(path)
+    assert torch.load(path) == [(5, 2)]
+
+
+def test_generate_patch_is_reversible():
+    from transformers import GenerationMixin
+    import lade
+    from lookaheaddecoding_b200.decoding import sample_entry_proxy
+    original = GenerationMixin._sample
+    lade.augment_generate()
+    try:
+        assert GenerationMixin._sample is sample_entry_proxy
+        lade.augment_generate()                                   # idempotent: the original is not lost
+        assert GenerationMixin._sample is sample_entry_proxy
+    finally:
+        lade.restore_generate()
+    assert GenerationMixin._sample is original
+
+
+def test_max_length_resolution():
+    from transformers import MaxLengthCriteria, StoppingCriteriaList
+    from lookaheaddecoding_b200.decoding import _max_length_from
+    from lookaheaddecoding_b200 import LadeError
+    crit = StoppingCriteriaList([MaxLengthCriteria(40), MaxLengthCriteria(32)])
+    assert _max_length_from(crit, None, 10) == 32
+    assert _max_length_from(None, 5, 10) == 15
+    assert _max_length_from(crit, 5, 10) == 15
+    with pytest.raises(LadeError):
+        _max_length_from(None, None, 10)
+
+
+def test_split_warpers_and_their_validation():
+    from transformers.generation.logits_process import (LogitsProcessorList, MinLengthLogitsProcessor,
+                                                        RepetitionPenaltyLogitsProcessor, TemperatureLogitsWarper,
+                                                        TopKLogitsWarper, TopPLogitsWarper, TypicalLogitsWarper)
+    from lookaheaddecoding_b200.sampling import _check_warpers, split_warpers
+    from lookaheaddecoding_b200 import LadeError
+    lp = LogitsProcessorList([RepetitionPenaltyLogitsProcessor(1.1), TemperatureLogitsWarper(0.8), TopKLogitsWarper(50),
+                              MinLengthLogitsProcessor(3, 2), TopPLogitsWarper(0.9)])
+    procs, warpers = split_warpers(lp)
+    assert [type(p).__name__ for p in procs] == ["RepetitionPenaltyLogitsProcessor", "MinLengthLogitsProcessor"]
+    assert [type(w).__name__ for w in warpers] == ["TemperatureLogitsWarper", "TopKLogitsWarper", "TopPLogitsWarper"]
+    _check_warpers(warpers)
+    with pytest.raises(LadeError, match="top_k=0.0 and top_p=1.0"):       # lade/decoding.py:377
+        _check_warpers(LogitsProcessorList([TypicalLogitsWarper(0.5)]))
+    assert split_warpers(None) == (LogitsProcessorList(), LogitsProcessorList())
+
+
+def test_use_lade_env_gate(monkeypatch):
+    from lookaheaddecoding_b200.decoding import _use_lade
+    monkeypatch.delenv("USE_LADE", raising=False)
+    assert not _use_lade()
+    monkeypatch.setenv("USE_LADE", "0")
+    assert not _use_lade()
+    monkeypatch.setenv("USE_LADE", "1")
+    assert _use_lade()
