@@ -401,6 +401,8 @@ class LookaheadEngine:
         queued = 0                    # steps queued so far
         step = 0                      # steps whose record has been read
         guard = max_new_tokens + self.N + 4
+        # lookahead parallelism keeps the synchronous loop: that is the configuration the multi-GPU NCCL runs validated
+        pipelined = self.pipeline_host and self.DW == 1
 
         def enqueue():
             nonlocal queued
@@ -415,7 +417,7 @@ class LookaheadEngine:
         enqueue()
         while True:
             certainly_last = (len(out) - P) + 1 >= max_new_tokens
-            if self.pipeline_host and len(inflight) == 1 and not certainly_last:
+            if pipelined and len(inflight) == 1 and not certainly_last:
                 enqueue()
             rec = self._wait_result(inflight.pop(0))
             self.last_records.append(rec)
