@@ -103,6 +103,7 @@ typedef struct LadeConfig {
 /* Allocates the device-resident decode state (window, n-gram pool, token buffers).
  * Replaces the python locals of jacobi_greedy_search_multilevel, lade/decoding.py:854-916. */
 int lade_ctx_create(const LadeConfig* cfg, LadeCtx** out);
+/* Frees the device state (the reference relies on python GC of the loop's locals, decoding.py:1221-1259). */
 int lade_ctx_destroy(LadeCtx* ctx);
 
 /* Start a generate() call: upload prompt ids and the initial lookahead window level 0
@@ -127,7 +128,9 @@ int lade_step_layout(LadeCtx* ctx, void* stream, int32_t q_pad, int32_t* ids_out
                      uint32_t* rowmask_out /* [q_pad][mask_words], nullable */, int32_t mask_words);
 
 /* Expected live row count of the upcoming step as a pure function of the step index (host side, no
- * sync): prefill = P + W+N-3 ; fill step k ; steady = (N-1)*(W+G).  Returns the count or <0. */
+ * sync): prefill = P + W+N-3 ; fill step k ; steady = (N-1)*(W+G).  Returns the count or <0.
+ * Mirrors the lengths of the tensors jforward_multilevel concatenates (modeling_llama.py:1458-1511) for the
+ * fill_level schedule of decoding.py:1038-1066. */
 int lade_step_rows_bound(const LadeConfig* cfg, int32_t n_prompt, int32_t step_index);
 
 /* ---- floating-point kernels of the decoder layer ---------------------------------------------- */
@@ -138,7 +141,8 @@ int lade_step_rows_bound(const LadeConfig* cfg, int32_t n_prompt, int32_t step_i
 int lade_rmsnorm(void* stream, const void* x, const void* delta /*nullable*/, const void* weight,
                  void* h_out /*nullable unless delta*/, void* out, int32_t rows, int32_t hidden, float eps);
 
-/* Final-norm variant that gathers rows: out[i] = rmsnorm(x[rows_idx[i]] (+ delta[rows_idx[i]])). */
+/* Final-norm variant that gathers rows: out[i] = rmsnorm(x[rows_idx[i]] (+ delta[rows_idx[i]])).
+ * LlamaModel.norm (modeling_llama.py:1235) restricted to the rows whose logits the loop reads (:1570-1606). */
 int lade_rmsnorm_gather(void* stream, const void* x, const void* delta, const void* weight,
                         const int32_t* rows_idx, void* out, int32_t n_rows, int32_t hidden, float eps);
 
@@ -161,6 +165,8 @@ int lade_attn_fwd(void* stream, const void* q, const void* k_cache, const void* 
                   int32_t n_heads, int32_t n_kv_heads, int32_t head_dim, int32_t kv_capacity,
                   int32_t kv_bound /* host upper bound of kv_len + q_len */, int32_t n_splits,
                   int32_t impl /* 0 = default (= 2), 1 = mma.sync path, 2 = tcgen05/TMA path */);
+/* Bytes of zero-initialised scratch `lade_attn_fwd` needs for a shape (impl 1 keeps split partials there; the
+ * tcgen05 path merges inside the cluster and only needs the buffer to exist).  No reference counterpart. */
 int64_t lade_attn_scratch_bytes(int32_t q_pad, int32_t n_heads, int32_t head_dim, int32_t n_splits);
 /* Profiling aid: when set (device buffer of 8 int64 per CTA, or NULL to disable) the tcgen05 kernel records
  * clock64() at its phase boundaries (start, first K tile landed, first S ready, O final, partials written,
@@ -213,9 +219,11 @@ int lade_kv_compact(void* stream, const int32_t* result, void* k_base, void* v_b
                     int64_t layer_stride_elems, int32_t n_layers, int32_t n_kv_heads,
                     int32_t kv_capacity, int32_t head_dim, int32_t max_rows);
 
-/* Copy the generated ids (device) out: out_ids_dev int32[max_total_len]; count via result. */
+/* Copy the generated ids (device) out: out_ids_dev int32[max_total_len]; count via result.
+ * The reference returns them as `input_ids` grown by torch.cat each step (decoding.py:1165-1177,1221-1225). */
 int lade_ctx_output_ids(LadeCtx* ctx, void* stream, int32_t* out_host, int32_t n);
-/* Debug/test access to the device state (pool snapshot for parity tests). */
+/* Debug/test access to the device state: the n-gram pool (`token_map`, decoding.py:879) as cnt[V], tup[V][G][N-1]
+ * and the lookahead window (`past_tokens`, :887-902) as rows of W+N-3 ints with their live lengths. */
 int lade_ctx_pool_snapshot(LadeCtx* ctx, void* stream, int32_t* cnt_host, int32_t* tup_host);
 int lade_ctx_window_snapshot(LadeCtx* ctx, void* stream, int32_t* win_host, int32_t* len_host);
 
@@ -235,6 +243,8 @@ int lade_lp_verify(LadeCtx* ctx, void* stream, const int32_t* argmax_slots, cons
 int lade_lp_commit(LadeCtx* ctx, void* stream, const int32_t* records_all /* [D][record_ints] */,
                    const int32_t* meta, int32_t* result);
 
+/* Error text for a LADE_E* code / the last CUDA runtime error string seen by this library (the reference raises
+ * python exceptions or asserts, e.g. lade/utils.py:33, decoding.py:375-377,412); ABI version of this header. */
 const char* lade_strerror(int code);
 const char* lade_last_cuda_error(void);
 int lade_version(void);
