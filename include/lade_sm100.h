@@ -142,7 +142,7 @@ int lade_rmsnorm(void* stream, const void* x, const void* delta /*nullable*/, co
                  void* h_out /*nullable unless delta*/, void* out, int32_t rows, int32_t hidden, float eps);
 
 /* Final-norm variant that gathers rows: out[i] = rmsnorm(x[rows_idx[i]] (+ delta[rows_idx[i]])).
- * LlamaModel.norm (modeling_llama.py:1235) restricted to the rows whose logits the loop reads (:1570-1606). */
+ * LlamaModel.norm (modeling_llama.py:1240) restricted to the rows whose logits the loop reads (:1570-1606). */
 int lade_rmsnorm_gather(void* stream, const void* x, const void* delta, const void* weight,
                         const int32_t* rows_idx, void* out, int32_t n_rows, int32_t hidden, float eps);
 
@@ -222,8 +222,8 @@ int lade_kv_compact(void* stream, const int32_t* result, void* k_base, void* v_b
 /* Copy the generated ids (device) out: out_ids_dev int32[max_total_len]; count via result.
  * The reference returns them as `input_ids` grown by torch.cat each step (decoding.py:1165-1177,1221-1225). */
 int lade_ctx_output_ids(LadeCtx* ctx, void* stream, int32_t* out_host, int32_t n);
-/* Debug/test access to the device state: the n-gram pool (`token_map`, decoding.py:879) as cnt[V], tup[V][G][N-1]
- * and the lookahead window (`past_tokens`, :887-902) as rows of W+N-3 ints with their live lengths. */
+/* Debug/test access to the device state: the n-gram pool (`token_map`, decoding.py:911) as cnt[V], tup[V][G][N-1]
+ * and the lookahead window (`past_tokens`, :902) as rows of W+N-3 ints with their live lengths. */
 int lade_ctx_pool_snapshot(LadeCtx* ctx, void* stream, int32_t* cnt_host, int32_t* tup_host);
 int lade_ctx_window_snapshot(LadeCtx* ctx, void* stream, int32_t* win_host, int32_t* len_host);
 
