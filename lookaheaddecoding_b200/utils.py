@@ -17,32 +17,31 @@ from transformers import GenerationMixin
 from .decoding import CONFIG_MAP, FUNC_MAP, greedy_search_proxy, sample_entry_proxy, sample_proxy
 
 
+# Knobs that are plain CONFIG_MAP entries.  SPLIT_FLAG is a dead knob in the reference too (lade/utils.py:24-25);
+# USE_FLASH is accepted and ignored (the fused attention kernel is always on).
+_PLAIN_KNOBS = ("WINDOW_SIZE", "LEVEL", "GUESS_SET_SIZE", "ALWAYS_FWD_ONE", "DEBUG", "SPLIT_FLAG", "POOL_FROM_PROMPT",
+                "USE_FLASH")
+
+
+def _join_lookahead_workers(n_workers: int, backend: str) -> None:
+    """Lookahead parallelism set-up (lade/utils.py:28-33): one process per GPU, rank = LOCAL_RANK."""
+    local_rank = int(os.environ["LOCAL_RANK"])
+    CONFIG_MAP.update(DIST_WORKERS=n_workers, LOCAL_RANK=local_rank)
+    if not dist.is_initialized():
+        dist.init_process_group(backend, rank=local_rank)
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local_rank)
+    assert dist.get_world_size() == n_workers, "DIST_WORKERS config should be equal to work size"
+
+
 def config_lade(WINDOW_SIZE=None, LEVEL=None, DEBUG=None, GUESS_SET_SIZE=None, ALWAYS_FWD_ONE=None, SPLIT_FLAG=None,
                 DIST_WORKERS=None, POOL_FROM_PROMPT=None, backend='nccl', USE_FLASH=None):
-    if WINDOW_SIZE is not None:
-        CONFIG_MAP["WINDOW_SIZE"] = WINDOW_SIZE
-    if LEVEL is not None:
-        CONFIG_MAP["LEVEL"] = LEVEL
-    if GUESS_SET_SIZE is not None:
-        CONFIG_MAP["GUESS_SET_SIZE"] = GUESS_SET_SIZE
-    if ALWAYS_FWD_ONE is not None:
-        CONFIG_MAP["ALWAYS_FWD_ONE"] = ALWAYS_FWD_ONE
-    if DEBUG is not None:
-        CONFIG_MAP["DEBUG"] = DEBUG
-    if SPLIT_FLAG is not None:
-        CONFIG_MAP["SPLIT_FLAG"] = SPLIT_FLAG          # dead knob in the reference too (utils.py:24-25)
-    if POOL_FROM_PROMPT is not None:
-        CONFIG_MAP["POOL_FROM_PROMPT"] = POOL_FROM_PROMPT
+    """Same signature and semantics as lade/utils.py:13: every argument that is not None overwrites its CONFIG_MAP
+    entry, DIST_WORKERS > 1 joins the process group, and the step log is reset."""
+    given = locals()
+    CONFIG_MAP.update({knob: given[knob] for knob in _PLAIN_KNOBS if given[knob] is not None})
     if DIST_WORKERS is not None and DIST_WORKERS > 1:
-        CONFIG_MAP["DIST_WORKERS"] = DIST_WORKERS
-        CONFIG_MAP["LOCAL_RANK"] = int(os.environ["LOCAL_RANK"])
-        if not dist.is_initialized():
-            dist.init_process_group(backend, rank=CONFIG_MAP["LOCAL_RANK"])
-        if torch.cuda.is_available():
-            torch.cuda.set_device(CONFIG_MAP["LOCAL_RANK"])
-        assert dist.get_world_size() == DIST_WORKERS, "DIST_WORKERS config should be equal to work size"
-    if USE_FLASH is not None:
-        CONFIG_MAP["USE_FLASH"] = USE_FLASH            # accepted, ignored: the fused kernel is always on
+        _join_lookahead_workers(DIST_WORKERS, backend)
     CONFIG_MAP["log"] = []
 
 
@@ -80,17 +79,17 @@ def augment_all():
 
 
 def log_history(clear=False):
-    gen = 0
-    step = 0
-    if "log" in CONFIG_MAP:
-        for log in CONFIG_MAP["log"]:
-            gen += log[0]
-            step += log[1]
+    """Totals over the (generated tokens, steps) pairs logged by DEBUG runs; same report line as lade/utils.py:74-83."""
+    records = CONFIG_MAP.get("log", [])
+    gen, step = sum(r[0] for r in records), sum(r[1] for r in records)
     if clear:
         CONFIG_MAP["log"] = []
-    print("LADE LOG - OVERALL GEN: ", gen, " STEPS: ", step, " AVG COMPRESS RATIO: ", (gen / step) if step > 0 else 0)
+    ratio = (gen / step) if step > 0 else 0
+    print("LADE LOG - OVERALL GEN: ", gen, " STEPS: ", step, " AVG COMPRESS RATIO: ", ratio)
 
 
 def save_log(log_dir):
-    if "log" in CONFIG_MAP:
-        torch.save(CONFIG_MAP["log"], log_dir)
+    """torch.save of the step log, if any (lade/utils.py:85-87)."""
+    records = CONFIG_MAP.get("log")
+    if records is not None:
+        torch.save(records, log_dir)

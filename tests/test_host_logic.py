@@ -131,3 +131,27 @@ def test_use_lade_env_gate(monkeypatch):
     assert not _use_lade()
     monkeypatch.setenv("USE_LADE", "1")
     assert _use_lade()
+
+
+def test_config_lade_joins_lookahead_workers_over_gloo(tmp_path):
+    """config_lade(DIST_WORKERS=2, backend='gloo') under torchrun: process group joined, LOCAL_RANK recorded
+    (lade/utils.py:28-33), get_device()/distributed() answer like lade/lade_distributed.py."""
+    import subprocess
+    import sys
+    script = tmp_path / "join.py"
+    script.write_text(
+        "import os, sys\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import torch.distributed as dist\n"
+        "import lade\n"
+        "from lookaheaddecoding_b200.decoding import CONFIG_MAP\n"
+        "lade.config_lade(LEVEL=5, WINDOW_SIZE=15, GUESS_SET_SIZE=15, DIST_WORKERS=2, backend='gloo')\n"
+        "assert lade.distributed() and lade.get_device() == int(os.environ['LOCAL_RANK'])\n"
+        "assert CONFIG_MAP['DIST_WORKERS'] == 2 and CONFIG_MAP['LEVEL'] == 5 and CONFIG_MAP['log'] == []\n"
+        "dist.barrier()\n"
+        "print('LP_JOIN_OK') if dist.get_rank() == 0 else None\n"
+        "dist.destroy_process_group()\n")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29581", str(script)],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "LP_JOIN_OK" in res.stdout, res.stderr[-1500:]
