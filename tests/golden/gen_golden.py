@@ -71,6 +71,12 @@ def trace_reference_greedy(model, prompt, max_new, lade_cfg, py_seed=0, eos=None
         token_map_ref["tm"] = token_map
         return orig_utm(token_map, *a, **k)
 
+    orig_fill = decoding.fill_pool_with_prompt
+
+    def fill(prompts, token_map, *a, **k):      # runs before the loop (:915-916): runs that end before the window
+        token_map_ref["tm"] = token_map         # is full never reach update_token_map
+        return orig_fill(prompts, token_map, *a, **k)
+
     def mk(*a, **k):
         m = orig_mask(*a, **k)
         masks.append((m[0, 0] == 0))
@@ -129,12 +135,14 @@ def trace_reference_greedy(model, prompt, max_new, lade_cfg, py_seed=0, eos=None
 
     model.jforward_multilevel = fwd
     decoding.update_token_map = utm
+    decoding.fill_pool_with_prompt = fill
     modeling.j_make_causal_mask_multilevel = mk
     try:
         out = R.run_reference_greedy(model, prompt, max_new, lade_cfg, py_seed=py_seed, eos_token_id=eos)
     finally:
         model.jforward_multilevel = orig_fwd
         decoding.update_token_map = orig_utm
+        decoding.fill_pool_with_prompt = orig_fill
         modeling.j_make_causal_mask_multilevel = orig_mask
     tm = token_map_ref.get("tm", {})
     pool = {str(k): [list(t) for t in v] for k, v in tm.items()}

@@ -31,6 +31,39 @@ def rows_to_bool(rows):
     return np.array([[ch == "1" for ch in r] for r in rows], dtype=bool)
 
 
+def check_oracle_greedy_trace(c):
+    """Replay one reference run (golden trace dict `c`) through the oracle: every step's rows, guesses, argmax
+    tokens, KV bookkeeping and mask, then the output ids and the final pool must be identical."""
+    dtype = getattr(torch, c["dtype"])
+    w = LR.init_weights(c["model"], seed=c["weight_seed"], dtype=dtype)
+    om = LR.OracleLlama(c["model"], w)
+    trace, pool = [], {}
+    ids, steps = LA.greedy_lookahead(
+        c["prompt"], c["max_new"], c["W"], c["N"], c["G"], om.step_fn, om.compact_fn,
+        pool_from_prompt=c["pool_from_prompt"], eos_token_id=c["eos_token_id"],
+        rng=random.Random(c["py_seed"]), trace=trace, token_map_out=pool)
+    assert steps == c["n_steps"] == len(trace)
+    assert ids == c["output_ids"]
+    for i, (t, g) in enumerate(zip(trace, c["steps"])):
+        n_in = len(g["input_ids"]) if i == 0 else 1
+        flat = g["input_ids"][-n_in:]
+        for lvl in g["past_tokens"][: g["fill_level"] + 1]:
+            flat = flat + lvl
+        flat = flat + (g["guess_tokens"] or [])
+        assert t.ids == flat, f"step {i} rows"
+        assert t.guess_tokens == g["guess_tokens"], f"step {i} guesses"
+        assert t.first_guess == g["first_guess"] and t.inp_tokens == g["inp_tokens"], f"step {i} argmax"
+        assert t.guess_results == g["guess_results"], f"step {i} guess argmax"
+        assert t.kv_len + n_in == g["kvcache_len"] and t.kv_len + len(t.ids) == g["step_len"]
+        if g["mask_rows"] is not None:
+            lay = LA.layout_from_shape(t.level_sizes, n_in, len(t.guess_tokens or []), c["N"] - 1,
+                                       is_prefill=(i == 0))
+            want = rows_to_bool(g["mask_rows"])
+            np.testing.assert_array_equal(LA.step_mask(lay), want[:, t.kv_len:], err_msg=f"step {i} mask")
+    got_pool = {str(k): [list(t) for t in v] for k, v in pool.items()}
+    assert got_pool == c["final_pool"]
+
+
 def test_mask_predicate_matches_reference_builder():
     """oracle.row_sees == j_make_causal_mask_multilevel (modeling_llama.py:115) on 100+ shapes incl. LP."""
     masks = load_masks()
@@ -61,35 +94,7 @@ def test_media_mask_png_kat():
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_greedy_trace_matches_reference(name):
     """Step-by-step equality of the restated loop + model with the reference's own run."""
-    c = CASES[name]
-    dtype = getattr(torch, c["dtype"])
-    w = LR.init_weights(c["model"], seed=c["weight_seed"], dtype=dtype)
-    om = LR.OracleLlama(c["model"], w)
-    trace, pool = [], {}
-    ids, steps = LA.greedy_lookahead(
-        c["prompt"], c["max_new"], c["W"], c["N"], c["G"], om.step_fn, om.compact_fn,
-        pool_from_prompt=c["pool_from_prompt"], eos_token_id=c["eos_token_id"],
-        rng=random.Random(c["py_seed"]), trace=trace, token_map_out=pool)
-    assert steps == c["n_steps"] == len(trace)
-    assert ids == c["output_ids"]
-    for i, (t, g) in enumerate(zip(trace, c["steps"])):
-        n_in = len(g["input_ids"]) if i == 0 else 1
-        flat = g["input_ids"][-n_in:]
-        for lvl in g["past_tokens"][: g["fill_level"] + 1]:
-            flat = flat + lvl
-        flat = flat + (g["guess_tokens"] or [])
-        assert t.ids == flat, f"step {i} rows"
-        assert t.guess_tokens == g["guess_tokens"], f"step {i} guesses"
-        assert t.first_guess == g["first_guess"] and t.inp_tokens == g["inp_tokens"], f"step {i} argmax"
-        assert t.guess_results == g["guess_results"], f"step {i} guess argmax"
-        assert t.kv_len + n_in == g["kvcache_len"] and t.kv_len + len(t.ids) == g["step_len"]
-        if g["mask_rows"] is not None:
-            lay = LA.layout_from_shape(t.level_sizes, n_in, len(t.guess_tokens or []), c["N"] - 1,
-                                       is_prefill=(i == 0))
-            want = rows_to_bool(g["mask_rows"])
-            np.testing.assert_array_equal(LA.step_mask(lay), want[:, t.kv_len:], err_msg=f"step {i} mask")
-    got_pool = {str(k): [list(t) for t in v] for k, v in pool.items()}
-    assert got_pool == c["final_pool"]
+    check_oracle_greedy_trace(CASES[name])
 
 
 def test_position_ids_match_reference():
