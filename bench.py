@@ -55,6 +55,12 @@ def parse():
     ap.add_argument("--do-sample", action="store_true",
                     help="BASELINE.json configs[2]: sampling, temperature 0.8, top_k=0, top_p=1.0 (lade/decoding.py:137)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the AR series and the extra BASELINE configs (7B sampling, 13B, periodic-text weights)")
+    ap.add_argument("--weights", default="random", choices=["random", "cyclic"],
+                    help="cyclic: o_proj/down_proj zeroed -> periodic text, n-gram hits (see build_model)")
+    ap.add_argument("--ref-budget-s", type=float, default=240.0,
+                    help="--impl reference: wall-clock bound of the timed steady steps")
     ap.add_argument("--no-reference-cuda", action="store_true",
                     help="skip timing the unmodified reference's CUDA-eager loop (needs baseline/_ref)")
     ap.add_argument("--cuda-profiler-range", action="store_true",
@@ -72,27 +78,68 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons during the timed region (B200_PROFILING.md recipe), sampled IN-PROCESS through NVML
+    (nvidia_ml_py) every 0.25 s.  Round 1 spawned `nvidia-smi` every 200 ms; on the 8-GPU node each spawn enumerates
+    all boards and the end-to-end leg lost half its throughput there.  Falls back to the subprocess at 1 Hz when NVML
+    cannot be loaded."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
+        self.rows = []          # (sm_mhz, sm_max_mhz, reason_bits)
         self._stop = threading.Event()
         self._t = None
+        self._h = None
+        self._nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._nv, self._h = pynvml, h
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nv = None
+
+    def _sample_nvml(self):
+        nv, h = self._nv, self._h
+        sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+        try:
+            bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+        except Exception:
+            bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        self.rows.append((sm, self._max, bits))
+
+    def _sample_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+            r = [x.strip() for x in out.split(",")]
+            bits = 0
+            for bit, v in zip((0x8, 0x40, 0x20, 0x4), r[2:6]):
+                if v.lower().startswith("active"):
+                    bits |= bit
+            self.rows.append((float(r[0]), float(r[1]), bits))
 
     def _run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                if self._nv is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.25 if self._nv is not None else 1.0)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -104,23 +151,22 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                continue
-        if not sm:
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        sm = sorted(r[0] for r in self.rows)
+        bits = 0
+        for r in self.rows:
+            bits |= r[2]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(r[1] for r in self.rows),
+                "reasons": sorted(n for b, n in self.REASONS.items() if bits & b), "samples": len(sm),
+                "source": "nvml" if self._nv is not None else "nvidia-smi"}
 
 
-def build_model(shape, device):
+def build_model(shape, device, seed=0, weights="random"):
+    """HF LlamaForCausalLM of `shape`, random init normal(0, 0.02) (modeling_llama.py:934-943), bf16.
+    weights="cyclic": o_proj and down_proj are zeroed, so every layer is the identity on the residual stream and the
+    next token is a deterministic function of the last one -- the text becomes periodic, n-grams repeat, and the
+    verification branch / kv_compact / pool lookups do real work.  Bytes and FLOPs per step are unchanged."""
     import torch
     from transformers import LlamaConfig, LlamaForCausalLM
 
@@ -133,11 +179,13 @@ def build_model(shape, device):
     with torch.device("meta"):
         model = LlamaForCausalLM(cfg)
     model = model.to_empty(device=device).to(torch.bfloat16)
-    g = torch.Generator(device=device).manual_seed(0)
+    g = torch.Generator(device=device).manual_seed(seed)
     with torch.no_grad():
         for name, p in model.named_parameters():      # normal(0, initializer_range) as modeling_llama.py:934-943
             if p.dim() >= 2:
                 p.normal_(0.0, 0.02, generator=g)
+                if weights == "cyclic" and (name.endswith("o_proj.weight") or name.endswith("down_proj.weight")):
+                    p.zero_()
             else:
                 p.fill_(1.0)
         if hasattr(model.model, "rotary_emb"):
@@ -269,116 +317,196 @@ def usable_cores() -> int:
     return n
 
 
-def cpu_baseline(shape, W, N, G, n_threads, budget_layers=(1, 3), prompt_len=64, max_new=12):
-    """Oracle port of the reference loop (oracle/, reference eager numerics) on the host cores, on a bounded
-    sample: full widths, `budget_layers` decoder layers, short prompt.  Every forward step is timed on its own and
-    the MEDIAN steady step per depth is used (128 host threads are noisy); the per-layer cost is the difference of
-    the two depths and the full-depth step is extrapolated linearly (t = t[l1] + per_layer * (L - l1))."""
+class _EnoughSteps(Exception):
+    pass
+
+
+def reference_cpu(shape, W, N, G, P, max_new, n_threads, timed_steps=8, warm_steps=2, budget_s=240.0, weights="random"):
+    """The UNMODIFIED reference (baseline/_ref, loaded by baseline/ref_loader.py with the shims of SURVEY App. C)
+    running its own `jacobi_greedy_search_multilevel` (lade/decoding.py:697) on the HOST cores at the full stated
+    config: full depth, full widths, prompt P.  Bounded sample: the prefill step and the N-3 window-fill steps are
+    timed once, then `warm_steps` untimed + up to `timed_steps` timed STEADY decode steps (all identical in shape);
+    the run is aborted from a forward hook once enough steps are in (or `budget_s` is spent, never below 3 steps).
+    tokens/s of the whole workload = max_new / (t_prefill + t_fill + n_steady * mean(steady step)).
+    Each step time is a full loop iteration (model forward + the reference's python token selection / pool update)."""
     import statistics
     import torch
-    from oracle import llama_ref as LR
-    from oracle import lookahead as LA
-
-    torch.set_num_threads(n_threads)
-    med = {}
-    toks = steps = 0
-    # untimed warm-up (oneDNN primitive creation, thread pools) so that the first timed depth is not inflated
-    _w = LR.init_weights(dict(shape, layers=1), seed=0, dtype=torch.bfloat16)
-    _om = LR.OracleLlama(dict(shape, layers=1), _w)
-    LA.greedy_lookahead(list(range(3, 3 + 16)), 2, W, N, G, _om.step_fn, _om.compact_fn, rng=random.Random(0))
-    del _om, _w
-    for L in budget_layers:
-        cfg = dict(shape, layers=L)
-        w = LR.init_weights(cfg, seed=0, dtype=torch.bfloat16)
-        om = LR.OracleLlama(cfg, w)
-        g = torch.Generator().manual_seed(1)
-        prompt = torch.randint(3, shape["vocab"], (prompt_len,), generator=g).tolist()
-        durations = []
-
-        def timed_step(*a, _f=om.step_fn, **k):
-            t0 = time.perf_counter()
-            r = _f(*a, **k)
-            durations.append(time.perf_counter() - t0)
-            return r
-
-        out, st = LA.greedy_lookahead(prompt, max_new, W, N, G, timed_step, om.compact_fn, rng=random.Random(0))
-        steady = durations[N - 1:] if len(durations) > N + 1 else durations     # drop prefill + window-fill steps
-        med[L] = statistics.median(steady)
-        toks, steps = len(out) - prompt_len, st
-        del om, w
-    (l1, l2) = budget_layers
-    per_layer = (med[l2] - med[l1]) / (l2 - l1)
-    note = ""
-    if per_layer <= 0:                      # noise larger than the signal: fall back to an upper bound per layer
-        per_layer = med[l2] / l2
-        note = " (depth difference non-positive: per-layer cost taken as t/L of the deeper sample)"
-    t_full = med[l1] + per_layer * (shape["layers"] - l1)
-    return {"value": round((toks / steps) / t_full, 4), "unit": "tokens/s", "cores": n_threads, "kind": "port",
-            "sample": f"oracle port (reference eager numerics) on CPU: full widths, {l1} and {l2} of {shape['layers']} layers, "
-                      f"P={prompt_len}, {max_new} new tokens ({steps} steps); median steady forward step "
-                      f"{med[l1]:.3f}s@{l1}L, {med[l2]:.3f}s@{l2}L -> {per_layer:.3f}s/layer -> {t_full:.2f}s/step{note}, "
-                      f"{toks / steps:.2f} tokens/step"}
-
-
-def reference_cuda_eager(shape, W, N, G, P, max_new, device):
-    """The UNMODIFIED reference (pip-installed into the git-ignored baseline/_ref, loaded through the App.-C shims of
-    oracle/ref_shim.py) running its own eager lookahead loop on the same GPU: the denominator of BASELINE.json's
-    ">= 1.8x over the reference's own CUDA eager lookahead".  Extra reporting only; skipped when baseline/_ref is absent."""
-    import torch
-    ref_root = os.path.join(ROOT, "baseline", "_ref")
-    if not os.path.isfile(os.path.join(ref_root, "lade", "decoding.py")):
-        return {"unavailable": "baseline/_ref not present"}
-    os.environ["LADE_REFERENCE_ROOT"] = ref_root
-    import importlib
-    from oracle import ref_shim as R
-    importlib.reload(R)
+    from baseline import ref_loader as R
     from transformers import GenerationConfig, MaxLengthCriteria, StoppingCriteriaList
+
+    if not R.reference_available():
+        return {"unavailable": "baseline/_ref not present"}
+    torch.set_num_threads(n_threads)
     decoding, modeling = R.load_reference()
     cfg = R.make_llama_config(hidden=shape["hidden"], layers=shape["layers"], heads=shape["heads"], kv_heads=shape["kv_heads"],
                               inter=shape["inter"], vocab=shape["vocab"], max_pos=shape["max_pos"],
                               rope_theta=shape["rope_theta"], eps=shape["eps"])
     old_dtype = torch.get_default_dtype()
     torch.set_default_dtype(torch.bfloat16)
-    torch.set_default_device(device)          # also makes the mask builder's torch.tensor([...]) land on the GPU
+    t_build = time.perf_counter()
     try:
-        torch.manual_seed(0)
-        model = modeling.LlamaForCausalLM(cfg).eval()
+        with torch.device("meta"):
+            model = modeling.LlamaForCausalLM(cfg)
+        model = model.to_empty(device="cpu")
+        # normal(0, 0.02) values are drawn ONCE (2^24 of them) and tiled into every matrix at a per-tensor offset:
+        # drawing 6.7 G values with the CPU generator alone takes minutes, and GEMM time does not depend on the values
+        g = torch.Generator().manual_seed(0)
+        bank = (torch.randn(1 << 24, generator=g, dtype=torch.float32) * 0.02).to(torch.bfloat16)
         with torch.no_grad():
-            for p_ in model.parameters():
+            for k, (name, p_) in enumerate(model.named_parameters()):
                 if p_.dim() >= 2:
-                    p_.normal_(0.0, 0.02)
+                    if weights == "cyclic" and (name.endswith("o_proj.weight") or name.endswith("down_proj.weight")):
+                        p_.zero_()
+                        continue
+                    flat = p_.view(-1)
+                    off = (k * 1000003) % (bank.numel() // 2)
+                    pos = 0
+                    while pos < flat.numel():
+                        n = min(bank.numel() - off, flat.numel() - pos)
+                        flat[pos:pos + n].copy_(bank[off:off + n])
+                        pos += n
+                        off = 0
+                else:
+                    p_.fill_(1.0)
+        for mod in model.modules():          # rotary tables were left uninitialised by to_empty()
+            if hasattr(mod, "_set_cos_sin_cache") and hasattr(mod, "inv_freq"):
+                inv = 1.0 / (mod.base ** (torch.arange(0, mod.dim, 2).float() / mod.dim))
+                mod.register_buffer("inv_freq", inv, persistent=False)
+                mod._set_cos_sin_cache(seq_len=mod.max_position_embeddings, device="cpu", dtype=torch.bfloat16)
+        model.eval()
         model.generation_config = GenerationConfig(pad_token_id=0, eos_token_id=None)
+        t_build = time.perf_counter() - t_build
         torch.manual_seed(1)
-        prompt = torch.randint(3, shape["vocab"], (1, P), device=device)
+        prompt = torch.randint(3, shape["vocab"], (1, P))
+        n_pre = N - 2                                   # prefill + N-3 window-fill steps
+        marks = []
+        t_start = [0.0]
+        inner = model.jforward_multilevel
 
-        def run(n_new):
-            decoding.CONFIG_MAP.clear()
-            decoding.CONFIG_MAP.update(dict(WINDOW_SIZE=W, LEVEL=N, GUESS_SET_SIZE=G, DEBUG=1, log=[]))
-            random.seed(0)
-            with torch.no_grad():
-                out = decoding.jacobi_greedy_search_multilevel(
-                    model, prompt, stopping_criteria=StoppingCriteriaList([MaxLengthCriteria(P + n_new)]),
+        def hooked(*a, **k):
+            now = time.perf_counter()
+            marks.append(now)
+            steady_done = len(marks) - 1 - n_pre - warm_steps      # completed timed steady steps
+            if steady_done >= timed_steps or (steady_done >= 3 and now - t_start[0] > budget_s):
+                raise _EnoughSteps()
+            return inner(*a, **k)
+
+        model.jforward_multilevel = hooked
+        decoding.CONFIG_MAP.clear()
+        decoding.CONFIG_MAP.update(dict(WINDOW_SIZE=W, LEVEL=N, GUESS_SET_SIZE=G, DEBUG=0, log=[]))
+        random.seed(0)
+        t_start[0] = time.perf_counter()
+        import contextlib, io
+        try:
+            with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+                decoding.jacobi_greedy_search_multilevel(
+                    model, prompt, stopping_criteria=StoppingCriteriaList([MaxLengthCriteria(P + max_new)]),
                     attention_mask=torch.ones_like(prompt), use_cache=True, return_dict_in_generate=False,
                     output_attentions=False, output_hidden_states=False, output_scores=False, pad_token_id=0,
                     eos_token_id=None)
-            return out.shape[1] - P, decoding.CONFIG_MAP["log"][-1][1]
-        import contextlib, io
-        with contextlib.redirect_stdout(io.StringIO()):
-            run(4)                                  # warm-up (minimal.py:30)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            toks, steps = run(max_new)
-            torch.cuda.synchronize()
-            dt = time.perf_counter() - t0
-        del model
-        torch.cuda.empty_cache()
-        return {"value": round(toks / dt, 2), "unit": "tokens/s", "tokens": toks, "decode_steps": steps,
-                "ms_per_decode_step": round(1e3 * dt / steps, 3), "accepted_tokens_per_step": round(toks / steps, 3),
-                "source": "unmodified reference (baseline/_ref, shims of SURVEY App. C), eager attention, same GPU, same "
-                          "shape/prompt length/seeds; wall clock around one generate after a warm-up (minimal.py:34-45)"}
+            marks.append(time.perf_counter())           # the run ended by itself (short max_new)
+        except _EnoughSteps:
+            pass
     finally:
         torch.set_default_dtype(old_dtype)
-        torch.set_default_device("cpu")
+    dur = [b - a for a, b in zip(marks[:-1], marks[1:])]           # full loop iterations
+    t_prefill = dur[0]
+    t_fill = sum(dur[1:n_pre])
+    steady = dur[n_pre + warm_steps:]
+    if len(steady) < 1:
+        return {"unavailable": f"too few steps timed ({len(dur)})"}
+    mean_steady = sum(steady) / len(steady)
+    # random-init weights on a random prompt accept exactly 1 token per step (the GPU arm reports the same); under
+    # `cyclic` weights the acceptance of the sample is not representative of the whole run, so it is not extrapolated
+    n_steady = max_new - n_pre
+    total_s = t_prefill + t_fill + n_steady * mean_steady
+    return {"value": round(max_new / total_s, 4), "unit": "tokens/s", "cores": n_threads, "kind": "reference",
+            "s_per_steady_step": round(mean_steady, 4), "steady_steps_timed": len(steady),
+            "steady_min_s": round(min(steady), 4), "steady_max_s": round(max(steady), 4),
+            "steady_stdev_s": round(statistics.pstdev(steady), 4), "prefill_s": round(t_prefill, 3),
+            "window_fill_s": round(t_fill, 3), "model_build_s": round(t_build, 1), "accepted_tokens_per_step": 1.0,
+            "sample": f"UNMODIFIED reference (baseline/_ref) jacobi_greedy_search_multilevel on {n_threads} host threads, bf16, "
+                      f"full depth ({shape['layers']} layers) and widths, prompt {P}: prefill step {t_prefill:.1f}s + {n_pre - 1} "
+                      f"window-fill steps {t_fill:.1f}s timed once, {warm_steps} untimed + {len(steady)} timed steady steps "
+                      f"(mean {mean_steady:.3f}s, min {min(steady):.3f}, max {max(steady):.3f}); whole workload "
+                      f"= {max_new} tokens / (prefill + fill + {n_steady} x mean steady step) at 1.0 accepted tokens/step"}
+
+
+def reference_cuda_eager(ref_model, shape, W, N, G, prompt_list, max_new):
+    """The UNMODIFIED reference (baseline/_ref) running its own eager lookahead loop on the same GPU and the SAME weight
+    tensors as our engine: the denominator of BASELINE.json's ">= 1.8x over the reference's own CUDA eager lookahead".
+    Returns (report, ids of the timed run)."""
+    import torch
+    from baseline import parity as PAR
+
+    PAR.reference_greedy(ref_model, prompt_list, 4, W, N, G, py_seed=0)           # warm-up (minimal.py:30)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ids, steps = PAR.reference_greedy(ref_model, prompt_list, max_new, W, N, G, py_seed=0)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    toks = len(ids) - len(prompt_list)
+    return {"value": round(toks / dt, 2), "unit": "tokens/s", "tokens": toks, "decode_steps": steps,
+            "ms_per_decode_step": round(1e3 * dt / steps, 3), "accepted_tokens_per_step": round(toks / steps, 3),
+            "source": "unmodified reference (baseline/_ref, shims of SURVEY App. C), eager attention, same GPU, same weight "
+                      "tensors / prompt / seeds; wall clock around one generate after a warm-up (minimal.py:34-45)"}, ids
+
+
+def time_generates(run_once, n, P, eng, dev):
+    """n device-timed generate() calls; returns (tokens, steps, ms)."""
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    toks = steps = 0
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        out = run_once()
+        toks += len(out) - P
+        steps += eng.last_steps
+    e1.record()
+    torch.cuda.synchronize()
+    return toks, steps, e0.elapsed_time(e1)
+
+
+def extra_workload(name, args, dev, do_sample=False, model=None, reps=3):
+    """One more BASELINE.json config measured in the same process (device-timed generate() calls + its own attention
+    roofline): configs[2] (7B sampling, T=0.8) and configs[3] (CodeLlama-13B shape, W20 N7 G20)."""
+    import torch
+    from lookaheaddecoding_b200 import LookaheadEngine
+    shape, W, N, G, P = WORKLOADS[name]
+    own = model is None
+    if own:
+        model = build_model(shape, dev)
+    eng = LookaheadEngine(model, W, N, G, max_total_len=P + args.max_new)
+    torch.manual_seed(1)
+    prompt = torch.randint(3, shape["vocab"], (1, P))[0].tolist()
+    if do_sample:
+        from transformers.generation.logits_process import LogitsProcessorList, TemperatureLogitsWarper
+        from lookaheaddecoding_b200.sampling import sample_lookahead
+        warper = LogitsProcessorList([TemperatureLogitsWarper(0.8)])
+
+        def run_once():
+            torch.manual_seed(2)
+            return sample_lookahead(eng, prompt, args.max_new, warper, rng=random.Random(0))
+    else:
+        def run_once():
+            return eng.generate(prompt, args.max_new, rng=random.Random(0))
+    for _ in range(2):
+        run_once()
+    toks, steps, ms = time_generates(run_once, reps, P, eng, dev)
+    roof = attn_roofline(eng, shape)
+    rep = {"workload": f"{WORKLOAD_NAMES[name]}{' -> sampling temp=0.8 top_k=0 top_p=1.0' if do_sample else ''}, W={W} N={N} "
+                       f"G={G}, prompt {P}, {args.max_new} new tokens", "value": round(toks / (ms * 1e-3), 2),
+           "unit": "tokens/s", "generates_timed": reps, "ms_per_decode_step": round(ms / steps, 4),
+           "accepted_tokens_per_step": round(toks / steps, 3), "attn_splits": eng.attn_splits, "roofline": roof}
+    eng.close()
+    del eng
+    if own:
+        model.__dict__.pop("_lade_fused", None)
+        model.__dict__.pop("_lade_engines", None)
+        del model
+    torch.cuda.empty_cache()
+    return rep
 
 
 def main():
@@ -391,6 +519,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     config = {"workload": f"{WORKLOAD_NAMES[args.workload]}, W={W} N={N} G={G}, prompt {P} tokens, {args.max_new} new tokens "
                           f"per generate()", "prompt_len": P, "max_new_tokens": args.max_new,
+              "weights": "random-init normal(0, 0.02)" if args.weights == "random" else
+              "random-init, o_proj/down_proj zeroed (periodic text: n-gram hits; same bytes/FLOPs)",
               "parallelism": "single" if world == 1 else
               f"lookahead parallelism x{world} (lade_distributed: window columns + guess n-grams sharded per rank, "
               f"one NCCL all-gather of a fixed int32 record per step; same W/G => total work fixed)",
@@ -401,24 +531,20 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        # The reference's own CPU implementation of the path = the oracle port on the host cores.  One "step" is one
-        # bounded sample (two shallow depths at full widths, extrapolated in depth); W untimed + K timed samples.
+        # The reference's own implementation of the path on the host cores: the UNMODIFIED reference from baseline/_ref
+        # at the stated config (full depth, P tokens of context).  One "step" of this arm = one steady decode step of
+        # its loop (a bounded sample of the workload); W untimed + K timed, the whole-workload tokens/s follows from
+        # prefill + window fill (timed once) + (max_new - N + 2) steady steps.
         n_threads = usable_cores()
-        for _ in range(max(0, args.warmup)):
-            cpu_baseline(shape, W, N, G, n_threads, max_new=6)
-        samples, wall = [], []
-        for _ in range(max(1, args.steps)):
-            t0 = time.perf_counter()
-            samples.append(cpu_baseline(shape, W, N, G, n_threads))
-            wall.append(time.perf_counter() - t0)
-        vals = sorted(c["value"] for c in samples)
-        cb = dict(samples[len(samples) // 2])
-        cb["value"] = round(sum(vals) / len(vals), 4)
-        cb["sample"] += f"; mean of {len(vals)} samples (min {vals[0]}, max {vals[-1]})"
+        cb = reference_cpu(shape, W, N, G, P, args.max_new, n_threads, timed_steps=max(3, args.steps),
+                           warm_steps=max(0, args.warmup), budget_s=args.ref_budget_s, weights=args.weights)
+        if "unavailable" in cb:
+            print(json.dumps({"impl": "reference", "unavailable": cb["unavailable"]}))
+            return
         line = {"metric": metric, "value": cb["value"], "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": round(1e3 * sum(wall) / len(wall), 1), "higher_is_better": True,
+                "warmup": args.warmup, "ms_per_step": round(1e3 * cb["s_per_steady_step"], 1), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
-                "impl": "reference", "cpu_baseline": cb,
+                "impl": "reference", "accepted_tokens_per_step": cb["accepted_tokens_per_step"], "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -436,7 +562,7 @@ def main():
     import lade
     from lookaheaddecoding_b200.decoding import CONFIG_MAP, get_engine
 
-    model = build_model(shape, dev)
+    model = build_model(shape, dev, weights=args.weights)
     os.environ["USE_LADE"] = "1"
     lade.augment_all()
     lade.config_lade(LEVEL=N, WINDOW_SIZE=W, GUESS_SET_SIZE=G, DEBUG=0, DIST_WORKERS=world if world > 1 else None,
@@ -476,7 +602,7 @@ def main():
             return eng.generate(prompt_list, args.max_new, rng=random.Random(0))
         gen_kwargs = dict(do_sample=False)
     for _ in range(max(args.warmup, 1)):
-        run_once()
+        out_warm = run_once()
     barrier()
 
     # ---- device-timed: prompt already with the engine
@@ -500,9 +626,23 @@ def main():
         dev_ms = e0.elapsed_time(e1)
         launches = eng.launches - launches0
         # ---- end to end through the plugin surface: pinned host prompt -> generate() -> host ids
+        for _ in range(2):                                     # the HF generate() path has its own first-call costs
+            model.generate(prompt_host.to(dev), attention_mask=torch.ones(1, P, dtype=torch.long, device=dev),
+                           max_new_tokens=8, **gen_kwargs)
+        engine_s = [0.0]
+        if not args.do_sample:
+            inner_generate = eng.generate
+
+            def timed_generate(*a, **k):
+                t_ = time.perf_counter()
+                r_ = inner_generate(*a, **k)
+                engine_s[0] += time.perf_counter() - t_
+                return r_
+            eng.generate = timed_generate
         barrier()
         t0 = time.perf_counter()
         e2e_toks = 0
+        e2e_ids = None
         for _ in range(args.steps):
             random.seed(0)
             ids = prompt_host.to(dev, non_blocking=True)
@@ -511,30 +651,140 @@ def main():
             o = model.generate(ids, attention_mask=torch.ones_like(ids), max_new_tokens=args.max_new, **gen_kwargs)
             o_host = o.cpu()
             e2e_toks += o_host.shape[1] - P
+            e2e_ids = o_host[0].tolist()
         barrier()
         e2e_s = time.perf_counter() - t0
+        if not args.do_sample:
+            eng.generate = inner_generate
     t = torch.tensor([dev_ms, e2e_s, float(toks), float(e2e_toks), float(steps), float(launches)], device=dev, dtype=torch.float64)
+    lp_ids_equal = None
     if world > 1:
         mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         dev_ms, e2e_s = mx[0].item(), mx[1].item()
         launches = sm[5].item()          # kernels launched on all ranks; tokens/steps are one shared sequence
+        # ids under lookahead parallelism: every rank must hold the same sequence, and it must be the single-GPU one
+        # (decoding.py:1088-1107: LP changes who verifies what, never the greedy output)
+        mine = torch.tensor(out, device=dev, dtype=torch.int64)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        ranks_agree = all(bool((a_ == allr[0]).all()) for a_ in allr)
+        single = None
+        if rank == 0:
+            from lookaheaddecoding_b200 import LookaheadEngine
+            e1gpu = LookaheadEngine(model, W, N, G, max_total_len=P + args.max_new)
+            single = e1gpu.generate(prompt_list, args.max_new, rng=random.Random(0))
+            e1gpu.close()
+            del e1gpu
+            n_same = next((i for i in range(min(len(single), len(out))) if single[i] != out[i]), min(len(single), len(out)))
+            lp_ids_equal = {"ranks_agree": ranks_agree, "equal_to_single_gpu": single == out,
+                            "equal_prefix_tokens": n_same - P, "compared_tokens": len(out) - P}
+        dist.barrier()
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
-    roof = attn_roofline(eng, shape)
-    ref_cuda = None
-    if not args.no_reference_cuda and world == 1:
-        try:
-            ref_cuda = reference_cuda_eager(shape, W, N, G, P, args.max_new, dev)
-        except Exception as ex:   # reporting only
-            ref_cuda = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
     clocks = sampler.summary()
-    cb = None
-    if not args.no_cpu_baseline and world == 1:      # host-core baseline: rank 0 at N=1 only
+    roof = attn_roofline(eng, shape)
+
+    # ---- the unmodified reference on the same GPU and weights: timing + token-id parity
+    ref_cuda = parity = ar = None
+    extras = {}
+    if world == 1 and not args.do_sample and not args.no_reference_cuda:
         try:
-            cb = cpu_baseline(shape, W, N, G, usable_cores())
+            from baseline import parity as PAR
+            from baseline import ref_loader as RL
+            if not RL.reference_available():
+                ref_cuda = {"unavailable": "baseline/_ref not present"}
+            else:
+                ref_model = PAR.reference_model_sharing_weights(model, shape)
+                ref_cuda, ref_ids = reference_cuda_eager(ref_model, shape, W, N, G, prompt_list, args.max_new)
+                parity = PAR.compare_ids(lambda p_, n_: eng.generate(p_, n_, rng=random.Random(0)), ref_ids, P, ref_model)
+                parity["e2e_ids_equal_device_timed_ids"] = (e2e_ids == out)
+                del ref_model
+                torch.cuda.empty_cache()
+        except Exception as ex:   # reporting only
+            ref_cuda = ref_cuda or {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+            parity = parity or {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+
+    # ---- plain autoregressive series (BASELINE.md "AR"): at 1.0 accepted tokens/step lookahead is
+    # pure overhead, and only this line shows it.  Ours: the same engine with the smallest window (W=1, N=3, G=0: two
+    # rows per step, no verification).  Reference side: stock HF generate() on the same model (USE_LADE=0 -- what the
+    # reference's greedy_search_proxy falls back to, lade/decoding.py:15-26).
+    if world == 1 and not args.do_sample and not args.no_extras:
+        try:
+            from lookaheaddecoding_b200 import LookaheadEngine
+            ar_eng = LookaheadEngine(model, 1, 3, 0, max_total_len=P + args.max_new)
+            ar_run = lambda: ar_eng.generate(prompt_list, args.max_new, rng=random.Random(0))
+            ar_run()
+            a_toks, a_steps, a_ms = time_generates(ar_run, 2, P, ar_eng, dev)
+            ar_out = ar_run()
+            ar_eng.close()
+            del ar_eng
+            os.environ["USE_LADE"] = "0"
+            ids = prompt_host.to(dev)
+            am_ = torch.ones_like(ids)
+            model.generate(ids, attention_mask=am_, max_new_tokens=8, do_sample=False)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            hf_out = model.generate(ids, attention_mask=am_, max_new_tokens=args.max_new, do_sample=False)
+            torch.cuda.synchronize()
+            hf_s = time.perf_counter() - t0
+            os.environ["USE_LADE"] = "1"
+            hf_list = hf_out[0].tolist()
+            same = next((i for i in range(P, min(len(hf_list), len(out))) if hf_list[i] != out[i]), min(len(hf_list), len(out)))
+            ar = {"ours_min_window": {"value": round(a_toks / (a_ms * 1e-3), 2), "unit": "tokens/s",
+                                      "ms_per_decode_step": round(a_ms / a_steps, 4), "config": "W=1 N=3 G=0 (2 rows/step)",
+                                      "ids_equal_lookahead_ids": ar_out == out},
+                  "hf_generate": {"value": round((hf_out.shape[1] - P) / hf_s, 2), "unit": "tokens/s",
+                                  "ms_per_decode_step": round(1e3 * hf_s / max(hf_out.shape[1] - P, 1), 3),
+                                  "config": "transformers generate(), USE_LADE=0, same model object",
+                                  "ids_equal_prefix_vs_lookahead": same - P},
+                  "lookahead_over_own_ar": round((toks / (dev_ms * 1e-3)) / (a_toks / (a_ms * 1e-3)), 3)}
+        except Exception as ex:
+            os.environ["USE_LADE"] = "1"
+            ar = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+
+    # ---- BASELINE.json configs[2] (7B sampling) and configs[3] (13B W20 N7 G20) in the same run
+    if world == 1 and args.workload == "7b" and not args.do_sample and not args.no_extras and args.weights == "random":
+        for key, kw in (("7b_sampling", dict(name="7b", do_sample=True, model=model)), ("13b", dict(name="13b"))):
+            try:
+                extras[key] = extra_workload(args=args, dev=dev, **kw)
+            except Exception as ex:
+                extras[key] = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+        # ---- a workload on which lookahead DOES something: zero o_proj/down_proj in place -> the next
+        # token is a function of the last one, text turns periodic, n-grams hit.  Both arms, same weights.
+        try:
+            with torch.no_grad():
+                for layer in model.model.layers:
+                    layer.self_attn.o_proj.weight.zero_()
+                    layer.mlp.down_proj.weight.zero_()
+            run_once()
+            c_toks, c_steps, c_ms = time_generates(run_once, 3, P, eng, dev)
+            cyc = {"weights": "o_proj/down_proj zeroed (periodic text; bytes/FLOPs per step unchanged)",
+                   "value": round(c_toks / (c_ms * 1e-3), 2), "unit": "tokens/s",
+                   "accepted_tokens_per_step": round(c_toks / c_steps, 3), "ms_per_decode_step": round(c_ms / c_steps, 4),
+                   "kv_compact_steps": sum(1 for r_ in eng.last_records if r_.max_hit > 0)}
+            from baseline import parity as PAR
+            from baseline import ref_loader as RL
+            if RL.reference_available():
+                ref_model = PAR.reference_model_sharing_weights(model, shape)
+                rc, rids = reference_cuda_eager(ref_model, shape, W, N, G, prompt_list, args.max_new)
+                cyc["reference_cuda_eager"] = {k_: rc[k_] for k_ in ("value", "accepted_tokens_per_step", "ms_per_decode_step", "decode_steps")}
+                pr = PAR.compare_ids(lambda p_, n_: eng.generate(p_, n_, rng=random.Random(0)), rids, P, ref_model, max_divergences=16)
+                cyc["parity"] = {k_: pr[k_] for k_ in ("exact", "ok", "exact_prefix_tokens", "compared_tokens", "n_divergences",
+                                                       "worst_candidate_below_top_ulps")}
+                del ref_model
+            extras["7b_periodic"] = cyc
+        except Exception as ex:
+            extras["7b_periodic"] = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
+
+    cb = None
+    if not args.no_cpu_baseline and world == 1:      # host-core baseline: rank 0 at N=1 only, bounded sample
+        try:
+            cb = reference_cpu(shape, W, N, G, P, args.max_new, usable_cores(), timed_steps=8, warm_steps=2, budget_s=60.0)
         except Exception as ex:  # the baseline is reporting only; never hide the GPU numbers
-            cb = {"value": None, "unit": "tokens/s", "cores": usable_cores(), "kind": "port", "sample": f"failed: {ex}"}
+            cb = {"value": None, "unit": "tokens/s", "cores": usable_cores(), "kind": "reference", "sample": f"failed: {ex}"}
     value = toks / (dev_ms * 1e-3)
     line = {
         "metric": metric, "value": round(value, 2), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
@@ -544,8 +794,11 @@ def main():
         "accepted_tokens_per_step": round(toks / steps, 3), "decode_steps": int(steps),
         "ms_per_decode_step": round(dev_ms / steps, 4),
         "e2e": {"value": round(e2e_toks / e2e_s, 2), "unit": "tokens/s", "h2d_bytes_per_step": P * 8,
-                "d2h_bytes_per_step": (P + args.max_new) * 8 + int(steps / args.steps) * 48 * 4},
+                "d2h_bytes_per_step": (P + args.max_new) * 8 + int(steps / args.steps) * 48 * 4,
+                "outside_engine_ms_per_generate": None if args.do_sample else
+                round(1e3 * (e2e_s - engine_s[0]) / args.steps, 2)},
         "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cb, "reference_cuda_eager": ref_cuda,
+        "parity": parity, "ar": ar, "lp_ids": lp_ids_equal, "more_configs": extras or None,
         "clocks": clocks,
         "attn_impl": eng.attn_impl, "attn_splits": eng.attn_splits, "cuda_graph": eng.use_cuda_graph,
     }

@@ -323,10 +323,12 @@ int attn_fwd_mma_launch(cudaStream_t stream, const void* q, const void* k_cache,
   if (head_dim != ATT_D) return LADE_EUNSUPPORTED;
   const int q_tiles = (q_pad + ATT_BM - 1) / ATT_BM;
   const size_t smem = (size_t)2 * ATT_STAGES * ATT_BN * ATT_D * sizeof(__nv_bfloat16);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;   // the attribute is per device (context): one bit per ordinal
+  int cur_dev = 0;
+  LADE_CUDA_CHECK(cudaGetDevice(&cur_dev));
+  if (!((attr_devs >> (cur_dev & 63)) & 1ull)) {
     LADE_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_devs |= 1ull << (cur_dev & 63);
   }
   const long long rows_pad = (long long)q_tiles * ATT_BM;
   if ((long long)n_heads * q_tiles > ATTN_MAX_COUNTERS) return LADE_EUNSUPPORTED;

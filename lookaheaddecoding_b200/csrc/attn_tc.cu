@@ -548,10 +548,12 @@ int attn_fwd_tc_launch(cudaStream_t stream, const void* q, const void* k_cache, 
   if ((rc = get_tensor_map(q, q_pad, n_heads, &tmQ)) != LADE_OK) return rc;
   if ((rc = get_tensor_map(k_cache, kv_capacity, n_kv_heads, &tmK)) != LADE_OK) return rc;
   if ((rc = get_tensor_map(v_cache, kv_capacity, n_kv_heads, &tmV)) != LADE_OK) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;   // the attribute is per device (context): one bit per ordinal
+  int cur_dev = 0;
+  LADE_CUDA_CHECK(cudaGetDevice(&cur_dev));
+  if (!((attr_devs >> (cur_dev & 63)) & 1ull)) {
     LADE_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    attr_set = true;
+    attr_devs |= 1ull << (cur_dev & 63);
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(n_splits, n_heads, q_tiles);

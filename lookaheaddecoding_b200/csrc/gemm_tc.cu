@@ -300,10 +300,12 @@ static void fill_launch_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* att
 }
 
 static int ensure_func_attrs() {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_devs = 0;   // the attribute is per device (context): one bit per ordinal
+  int cur_dev = 0;
+  LADE_CUDA_CHECK(cudaGetDevice(&cur_dev));
+  if (!((attr_devs >> (cur_dev & 63)) & 1ull)) {
     LADE_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_LIMIT));
-    attr_set = true;
+    attr_devs |= 1ull << (cur_dev & 63);
   }
   return LADE_OK;
 }

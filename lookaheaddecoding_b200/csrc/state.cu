@@ -54,7 +54,7 @@ __device__ __forceinline__ int* st_win(int* st, const Dims& d, int level) { retu
 // `tup` points at GS ints readable by every lane.  lade/decoding.py:39-49.
 __device__ void pool_insert_warp(int* st, const Dims& d, int key, const int* tup) {
   const int lane = threadIdx.x & 31;
-  if (key < 0 || key >= d.V) return;
+  if (d.G <= 0 || key < 0 || key >= d.V) return;   // G = 0: no pool (and no slot to write: `last` would be -1)
   int* cnt = st + d.off_cnt;
   int* base = st + d.off_tup + (long long)key * d.G * d.GS;
   const int c = cnt[key];
@@ -96,14 +96,30 @@ __device__ void pool_insert_warp(int* st, const Dims& d, int key, const int* tup
 
 // ---- reset: pool from prompt ------------------------------------------------------------------
 __global__ void fill_pool_from_prompt_kernel(int* st, Dims d, int n_prompt) {
-  // sequential in prompt order (LRU order matters), lane-parallel inside one insertion
-  __shared__ int tup[64];
-  const int lane = threadIdx.x;
+  // Insertions with different keys touch disjoint pool rows; only the order WITHIN one key matters (LRU).
+  // Every warp of the grid walks the prompt in order, 32 positions per ballot, and performs the insertions
+  // whose key it owns (key % n_warps), lane-parallel inside one insertion -- P/n_warps serial steps per warp
+  // instead of P on a single warp.
+  __shared__ int tup_all[8][32];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  const int n_warps = gridDim.x * (blockDim.x >> 5);
+  const int me = blockIdx.x * (blockDim.x >> 5) + wib;
+  int* tup = tup_all[wib];
   const int* ids = st + d.off_out;
-  for (int s = 0; s + d.N <= n_prompt; ++s) {
-    if (lane < d.GS) tup[lane] = ids[s + 1 + lane];
-    __syncwarp();
-    pool_insert_warp(st, d, ids[s], tup);
+  const int n_pos = n_prompt - d.N + 1;
+  for (int s0 = 0; s0 < n_pos; s0 += 32) {
+    const int s = s0 + lane;
+    const int key = s < n_pos ? ids[s] : -1;
+    unsigned mine = __ballot_sync(0xffffffffu, key >= 0 && (key % n_warps) == me);
+    while (mine) {
+      const int src = __ffs(mine) - 1;
+      mine &= mine - 1;
+      const int sk = s0 + src;
+      if (lane < d.GS) tup[lane] = ids[sk + 1 + lane];
+      __syncwarp();
+      pool_insert_warp(st, d, ids[sk], tup);
+    }
   }
 }
 
@@ -643,7 +659,8 @@ static int make_dims(const LadeConfig& c, Dims* d) {
   d->D = c.dist_workers > 1 ? c.dist_workers : 1;
   d->rank = c.dist_workers > 1 ? c.rank : 0;
   if (d->D > 64 || d->rank < 0 || d->rank >= d->D) return LADE_EINVAL;
-  if (d->GS > 63 || d->W > 1024 || d->WCAP > 16384 || d->G > 4096) return LADE_EUNSUPPORTED;
+  // n-gram tuples are staged by one warp, one token per lane: LEVEL - 1 <= 32
+  if (d->GS > 32 || d->W > 1024 || d->WCAP > 16384 || d->G > 4096) return LADE_EUNSUPPORTED;
   d->lm_cap = 1 + d->WCAP + d->G * d->GS;
   long long off = S_HDR_INTS;
   d->off_win = (int)off; off += (long long)(d->N - 1) * d->WCAP;
@@ -704,7 +721,7 @@ int lade_ctx_reset(LadeCtx* ctx, void* stream, const int32_t* prompt_host, int32
   reset_header_kernel<<<1, 256, 0, s>>>(ctx->state, d, n_prompt, n_window0, max_length);
   LADE_LAUNCH_CHECK("reset_header_kernel");
   if (d.pool_from_prompt && d.G > 0) {
-    fill_pool_from_prompt_kernel<<<1, 32, 0, s>>>(ctx->state, d, n_prompt);
+    fill_pool_from_prompt_kernel<<<37, 256, 0, s>>>(ctx->state, d, n_prompt);   // 296 warps, keys sharded by id
     LADE_LAUNCH_CHECK("fill_pool_from_prompt_kernel");
   }
   return LADE_OK;

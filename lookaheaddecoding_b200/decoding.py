@@ -82,6 +82,31 @@ def _max_length_from(stopping_criteria, max_length, init_len) -> int:
     return int(best)
 
 
+def _extra_stopping_criteria(stopping_criteria):
+    """Criteria beyond max-length / EOS (both handled on device).  The reference evaluates the whole list on every step
+    (lade/decoding.py:1215, :646); anything else here is evaluated on the host after each step record."""
+    from transformers.generation.stopping_criteria import MaxLengthCriteria
+    try:
+        from transformers.generation.stopping_criteria import EosTokenCriteria
+    except ImportError:      # transformers 4.36 has no EosTokenCriteria
+        EosTokenCriteria = ()
+    handled = (MaxLengthCriteria,) + ((EosTokenCriteria,) if EosTokenCriteria else ())
+    return [c for c in (stopping_criteria or []) if not isinstance(c, handled)]
+
+
+def _host_stop_fn(extra, device, dtype):
+    if not extra:
+        return None
+
+    def stop(ids) -> bool:
+        t = torch.tensor([ids], dtype=dtype, device=device)
+        for crit in extra:
+            if bool(torch.as_tensor(crit(t, None)).all()):
+                return True
+        return False
+    return stop
+
+
 def get_engine(model, **overrides) -> LookaheadEngine:
     """One engine per (model, lookahead config); reads CONFIG_MAP like lade/decoding.py:854-862."""
     W = CONFIG_MAP.get("WINDOW_SIZE", 60)
@@ -89,7 +114,11 @@ def get_engine(model, **overrides) -> LookaheadEngine:
     N = CONFIG_MAP.get("LEVEL", 8)
     pool = bool(CONFIG_MAP.get("POOL_FROM_PROMPT", 0))
     overrides = {**CONFIG_MAP.get("ENGINE_OVERRIDES", {}), **overrides}
-    cap = int(overrides.pop("max_total_len", CONFIG_MAP.get("MAX_TOTAL_LEN", 4096)))
+    # capacity: at least the request, and at least MAX_TOTAL_LEN (default 4096) so that a later, longer request does not
+    # tear the engine down (KV cache + CUDA graphs) again
+    cap = max(int(overrides.pop("max_total_len", 0)), int(CONFIG_MAP.get("MAX_TOTAL_LEN", 4096)))
+    max_pos = int(getattr(model.config, "max_position_embeddings", cap) or cap)
+    cap = max(int(overrides.pop("min_total_len", 0)), min(cap, max(max_pos, 1)))
     if CONFIG_MAP.get("DIST_WORKERS", 1) > 1:                         # lookahead parallelism (lade/utils.py:28-33)
         overrides.setdefault("dist_workers", CONFIG_MAP["DIST_WORKERS"])
         overrides.setdefault("rank", CONFIG_MAP.get("LOCAL_RANK", 0))
@@ -97,8 +126,11 @@ def get_engine(model, **overrides) -> LookaheadEngine:
     cache = model.__dict__.setdefault("_lade_engines", {})
     eng = cache.get(key)
     if eng is None or eng.max_total_len < cap:
-        if eng is not None:
+        if eng is not None:          # drop the old engine (KV cache, graphs) BEFORE building the new one
             eng.close()
+            del cache[key]
+            eng = None
+            torch.cuda.empty_cache()
         eng = LookaheadEngine(model, W, N, G, pool_from_prompt=pool, max_total_len=cap, **overrides)
         cache[key] = eng
     return eng
@@ -135,9 +167,10 @@ def jacobi_greedy_search_multilevel(self, input_ids: torch.LongTensor, logits_pr
         raise ValueError("If `eos_token_id` is defined, make sure that `pad_token_id` is defined.")   # :1028-1029
     init_len = input_ids.shape[1]
     total = _max_length_from(stopping_criteria, max_length, init_len)
-    eng = get_engine(self, max_total_len=max(total, CONFIG_MAP.get("MAX_TOTAL_LEN", 0)))
+    eng = get_engine(self, max_total_len=total, min_total_len=total)
     prompt = input_ids[0].tolist()
-    out = eng.generate(prompt, total - init_len, eos_token_ids=eos_token_id or (), rng=random)
+    stop_fn = _host_stop_fn(_extra_stopping_criteria(stopping_criteria), input_ids.device, input_ids.dtype)
+    out = eng.generate(prompt, total - init_len, eos_token_ids=eos_token_id or (), rng=random, stop_fn=stop_fn)
     if streamer is not None:
         streamer.put(torch.tensor(out[init_len:]))
         streamer.end()

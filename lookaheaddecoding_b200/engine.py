@@ -103,15 +103,18 @@ class LookaheadEngine:
         probe = self._make_config(())
         self.q_steady = int(self.lib.lade_step_rows_bound(C.byref(probe), 1, self.N))    # fixed steady shape
         self.rec_ints = int(self.lib.lade_lp_record_ints(C.byref(probe)))
-        self.kv_capacity = self.max_total_len + self.q_steady + self.WCAP + 8
         sm = torch.cuda.get_device_properties(self.dev).multi_processor_count
         q_tiles = (self.q_steady + 127) // 128
         # one CTA per SM (TMEM/smem bound): keep the split grid within a single wave
         self.attn_splits = int(attn_splits) if attn_splits else max(1, min(8, sm // (self.nh * q_tiles)))   # <= 8: the splits of a head form a thread-block cluster
 
+        # non-prefill steps: the steady shape, or a window-fill step when it is larger (G = 0 and W < N-2 ...)
+        self.q_nonprefill = max([self.q_steady] + [int(self.lib.lade_step_rows_bound(C.byref(probe), 1, k))
+                                                   for k in range(1, self.N - 1)])
+        self.kv_capacity = self.max_total_len + self.q_nonprefill + self.WCAP + 8
         self._fuse_weights()
         self._rope_tables()
-        self._alloc(self.q_steady)
+        self._alloc(self.q_nonprefill)
         self._ctx = C.c_void_p()
         self._lcfg = None
         self._graph = None
@@ -133,25 +136,38 @@ class LookaheadEngine:
         self.norm_w = m.norm.weight
         self.lm_head = self.model.lm_head.weight
         self.w_qkv, self.w_o, self.w_gu, self.w_down, self.ln1, self.ln2 = [], [], [], [], [], []
+        # a previous engine of this model already fused: reuse its storage (no second 13 GB transient) as long as
+        # the HF parameters still point into it
+        prev = self.model.__dict__.get("_lade_fused")
         with torch.no_grad():
-            for layer in m.layers:
+            for li, layer in enumerate(m.layers):
                 a, mlp = layer.self_attn, layer.mlp
                 if getattr(a.q_proj, "bias", None) is not None:
                     raise LadeError("attention_bias=True is not supported")
-                qkv = torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], dim=0).contiguous()
                 nq, nk = a.q_proj.weight.shape[0], a.k_proj.weight.shape[0]
-                a.q_proj.weight.data = qkv[:nq]
-                a.k_proj.weight.data = qkv[nq:nq + nk]
-                a.v_proj.weight.data = qkv[nq + nk:]
-                gu = torch.cat([mlp.gate_proj.weight, mlp.up_proj.weight], dim=0).contiguous()
-                mlp.gate_proj.weight.data = gu[: self.I]
-                mlp.up_proj.weight.data = gu[self.I:]
+                qkv = gu = None
+                if prev is not None and li < len(prev[0]):
+                    pq, pg = prev[0][li], prev[1][li]
+                    if (pq.data_ptr() == a.q_proj.weight.data_ptr() and pq[nq:].data_ptr() == a.k_proj.weight.data_ptr()
+                            and pq[nq + nk:].data_ptr() == a.v_proj.weight.data_ptr()
+                            and pg.data_ptr() == mlp.gate_proj.weight.data_ptr()
+                            and pg[self.I:].data_ptr() == mlp.up_proj.weight.data_ptr()):
+                        qkv, gu = pq, pg
+                if qkv is None:
+                    qkv = torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], dim=0).contiguous()
+                    a.q_proj.weight.data = qkv[:nq]
+                    a.k_proj.weight.data = qkv[nq:nq + nk]
+                    a.v_proj.weight.data = qkv[nq + nk:]
+                    gu = torch.cat([mlp.gate_proj.weight, mlp.up_proj.weight], dim=0).contiguous()
+                    mlp.gate_proj.weight.data = gu[: self.I]
+                    mlp.up_proj.weight.data = gu[self.I:]
                 self.w_qkv.append(qkv)
                 self.w_gu.append(gu)
                 self.w_o.append(a.o_proj.weight)
                 self.w_down.append(mlp.down_proj.weight)
                 self.ln1.append(layer.input_layernorm.weight)
                 self.ln2.append(layer.post_attention_layernorm.weight)
+        self.model.__dict__["_lade_fused"] = (self.w_qkv, self.w_gu)
 
     def _rope_tables(self):
         # fp32 math then cast to the model dtype: lade/models/modeling_llama.py:240-256,:264-265
@@ -172,7 +188,7 @@ class LookaheadEngine:
         self.ids = torch.zeros(rows, **i32)
         self.pos = torch.zeros(rows, **i32)
         self.rowdesc = torch.zeros(rows, **i32)
-        self.mask_words = (max(self.q_steady, 32) + 31) // 32 + 1      # non-prefill steps are short
+        self.mask_words = (max(self.q_nonprefill, 32) + 31) // 32 + 1      # non-prefill steps are short
         self.rowmask = torch.zeros(self.mask_words * 32 * self.mask_words, **i32)
         self.meta = torch.zeros(_cabi.META_INTS, **i32)
         self.lm_rows = torch.zeros(self.lm_cap, **i32)
@@ -210,7 +226,9 @@ class LookaheadEngine:
         return c
 
     def _ensure_ctx(self, eos_ids: Sequence[int]):
-        eos_ids = list(eos_ids)[:4]
+        eos_ids = list(eos_ids)
+        if len(eos_ids) > 4:
+            raise LadeError(f"at most 4 eos_token_id values are supported on device (got {len(eos_ids)})")
         key = (tuple(eos_ids),)
         if self._lcfg is not None and self._ctx_key == key:
             return
@@ -235,12 +253,15 @@ class LookaheadEngine:
             pass
 
     # ------------------------------------------------------------------------------------------
-    def _launch_step(self, rows: int, stream: int, commit: bool = True):
+    def _launch_step(self, rows: int, stream: int, commit: bool = True, prefill: bool = False):
         """All launches of one step on `stream` for `rows` materialised rows (rows <= rows_cap).
         commit=False stops after the row-wise argmax (the sampling path decides on the host)."""
         lib, L = self.lib, self.L
         n = 0
-        mw = self.mask_words if rows <= self.mask_words * 32 else 0      # prefill-sized steps: causal, no rowmask
+        # prefill (step 0) is plain causal and carries no rowmask; every later step has one and must fit it
+        mw = 0 if prefill else self.mask_words
+        if mw and rows > (mw - 1) * 32:
+            raise LadeError(f"step of {rows} rows does not fit the {mw}-word row mask")
         check(lib.lade_step_layout(self._ctx, stream, rows, _ptr(self.ids), _ptr(self.pos), _ptr(self.rowdesc),
                                    _ptr(self.lm_rows), _ptr(self.meta), _ptr(self.rowmask) if mw else 0, mw),
               "lade_step_layout"); n += 1
@@ -344,7 +365,9 @@ class LookaheadEngine:
             rows = self.lib.lade_step_rows_bound(C.byref(self._lcfg), n_prompt, step)
             if rows < 0:
                 raise LadeError("lade_step_rows_bound failed")
-            self.launches += self._launch_step(min(rows, self.rows_cap), stream, commit=commit)
+            if rows > self.rows_cap:
+                raise LadeError(f"step {step} needs {rows} rows but the engine buffers hold {self.rows_cap}")
+            self.launches += self._launch_step(rows, stream, commit=commit, prefill=(step == 0))
         else:
             self._steady_graph(commit).replay()
             self.launches += self._graph[commit][1]
@@ -381,8 +404,11 @@ class LookaheadEngine:
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
     def generate(self, prompt_ids: Sequence[int], max_new_tokens: int, eos_token_ids: Sequence[int] = (),
-                 rng: Optional[random.Random] = None, window0: Optional[Sequence[int]] = None) -> List[int]:
-        """Greedy lookahead decoding; returns prompt + generated ids (trimmed to P + max_new_tokens)."""
+                 rng: Optional[random.Random] = None, window0: Optional[Sequence[int]] = None,
+                 stop_fn=None) -> List[int]:
+        """Greedy lookahead decoding; returns prompt + generated ids (trimmed to P + max_new_tokens).
+        `stop_fn(ids) -> bool`: host-evaluated stopping criteria beyond max-length / EOS, checked after every step
+        like lade/decoding.py:1215 (disables the one-step-deep host pipelining)."""
         prompt = [int(t) for t in prompt_ids]
         P = len(prompt)
         max_length = P + int(max_new_tokens)
@@ -402,7 +428,7 @@ class LookaheadEngine:
         step = 0                      # steps whose record has been read
         guard = max_new_tokens + self.N + 4
         # lookahead parallelism keeps the synchronous loop: that is the configuration the multi-GPU NCCL runs validated
-        pipelined = self.pipeline_host and self.DW == 1
+        pipelined = self.pipeline_host and self.DW == 1 and stop_fn is None
 
         def enqueue():
             nonlocal queued
@@ -423,7 +449,7 @@ class LookaheadEngine:
             self.last_records.append(rec)
             out.extend(rec.hits)
             step += 1
-            if rec.done:
+            if rec.done or (stop_fn is not None and stop_fn(out[:max_length])):
                 break
             if step > guard:
                 raise LadeError("decode loop did not terminate (device state corrupt?)")

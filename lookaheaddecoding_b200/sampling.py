@@ -44,7 +44,7 @@ def _check_warpers(logits_warper):
 
 @torch.no_grad()
 def sample_lookahead(eng, prompt: List[int], max_new_tokens: int, logits_warper, eos_token_ids=(),
-                     rng=None, window0=None) -> List[int]:
+                     rng=None, window0=None, stop_fn=None) -> List[int]:
     """Drive one sampling generate() on `eng` (a LookaheadEngine). Returns prompt + sampled ids."""
     if eng.DW != 1:
         raise LadeError("the sampling path has no lookahead parallelism (reference: replicas only)")
@@ -166,8 +166,8 @@ def sample_lookahead(eng, prompt: List[int], max_new_tokens: int, logits_warper,
         out.extend(hits[:n_emit])
         input_ids = torch.tensor([out], device=dev)
         step += 1
-        if rec.done or finished or len(out) >= max_length:
-            break
+        if rec.done or finished or len(out) >= max_length or (stop_fn is not None and stop_fn(out[:max_length])):
+            break                                                                          # :636-646
         if step > max_new_tokens + N + 4:
             raise LadeError("sampling loop did not terminate")
     eng.last_steps = step
@@ -198,11 +198,14 @@ def jacobi_sample_multilevel(self, input_ids: torch.LongTensor, logits_processor
     saved = CONFIG_MAP.get("DIST_WORKERS")
     try:
         CONFIG_MAP.pop("DIST_WORKERS", None)      # sampling: replicas only
-        eng = get_engine(self, max_total_len=max(total, CONFIG_MAP.get("MAX_TOTAL_LEN", 0)))
+        eng = get_engine(self, max_total_len=total, min_total_len=total)
     finally:
         if saved is not None:
             CONFIG_MAP["DIST_WORKERS"] = saved
-    out = sample_lookahead(eng, input_ids[0].tolist(), total - init_len, logits_warper, eos_token_id or (), rng=random)
+    from .decoding import _extra_stopping_criteria, _host_stop_fn
+    stop_fn = _host_stop_fn(_extra_stopping_criteria(stopping_criteria), input_ids.device, input_ids.dtype)
+    out = sample_lookahead(eng, input_ids[0].tolist(), total - init_len, logits_warper, eos_token_id or (), rng=random,
+                           stop_fn=stop_fn)
     if streamer is not None:
         streamer.put(torch.tensor(out[init_len:]))
         streamer.end()

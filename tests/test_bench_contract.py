@@ -1,4 +1,5 @@
-"""bench.py's reference arm (CPU, oracle port on the host cores) honours the driver's JSON contract."""
+"""bench.py's reference arm (the UNMODIFIED reference from baseline/_ref on the host cores) honours the driver's JSON
+contract.  Run on the tiny workload so that the CPU suite stays fast; the 7B line is the same code path."""
 import json
 import os
 import subprocess
@@ -26,7 +27,9 @@ def test_reference_arm_prints_one_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "tokens/s" and d["higher_is_better"] is True
     assert d["vs_baseline"] is None and d["gpu_launches"] == 0 and "workload" in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["value"] > 0
+    assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["value"] > 0
+    assert cb["steady_steps_timed"] >= 2 and cb["s_per_steady_step"] > 0 and "UNMODIFIED reference" in cb["sample"]
+    assert d["ms_per_step"] == round(1e3 * cb["s_per_steady_step"], 1)
     assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

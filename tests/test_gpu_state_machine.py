@@ -12,7 +12,22 @@ import torch
 from helpers import load_cases, make_lade_config, rows_to_bool
 
 pytestmark = pytest.mark.gpu
-CASES = load_cases()
+
+
+def _all_cases():
+    """The 10 regular traces + the 9 edge-case traces (1-token prompt, prompt < N, 1-2 new tokens, W=1, G=1, N=3 under a
+    wide window, EOS on the first token; tests/golden/gen_golden_edge.py)."""
+    import gzip
+    import json
+    import os
+    from helpers import GOLD
+    out = dict(load_cases())
+    with gzip.open(os.path.join(GOLD, "greedy_edge_traces.json.gz"), "rt") as f:
+        out.update(json.load(f)["cases"])
+    return out
+
+
+CASES = _all_cases()
 
 
 def _decode_rowdesc(rd):
