@@ -41,10 +41,11 @@ __device__ long long* g_attn_timing = nullptr;
 #define TC_STAMP(slot, tid) do { if (tbuf && threadIdx.x == (tid)) tbuf[slot] = clock64(); } while (0)
 enum { TS_START = 0, TS_KFULL0 = 1, TS_SFULL0 = 2, TS_OFINAL = 3, TS_STAGED = 4, TS_CLUSTER = 5, TS_MERGED = 6, TS_END = 7 };
 
+// Split merge staging (written by the sibling CTAs of the cluster through distributed shared memory, see the tail of the
+// kernel): slot k of an owner CTA = [rows_per_owner][TC_SO_STRIDE] floats of one sibling's unnormalised O quarter-rows.
 constexpr int TC_SO_STRIDE = 132;                       // floats per staged O row (528 B: conflict-free float4 rows)
-constexpr int TC_SO_OFFSET = TC_TILE_BYTES;             // staged O lives in the (dead) K/V stages
-constexpr int TC_SML_OFFSET = 0;                        // (m, l) per row: 1 KB in the (dead) Q tile
-constexpr int TC_SW_OFFSET = 4096;                      // merge weights [rows][cluster] <= 4 KB
+constexpr int TC_SO_OFFSET = TC_TILE_BYTES;             // slots live in the (dead) K/V stages: <= 7 * 16 * 528 B
+constexpr int TC_SML_OFFSET = 0;                        // (m, l) per slot and row: <= 7 * 64 * 8 B in the (dead) Q tile
 
 // ---- kernel ---------------------------------------------------------------------------------------------
 // grid (n_splits, heads, q tiles); when n_splits > 1 the n_splits CTAs of one (head, q tile) form a thread-block
@@ -65,11 +66,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   int Tm = T;
   if (is_prefill) Tm = min(T, kv_len + min(q_len, (mt + 1) * TC_BM));
   const int n_tiles = (Tm + TC_BN - 1) / TC_BN;
-  const int tps = (n_tiles + n_splits - 1) / n_splits;
-  const int n_active = (n_tiles + tps - 1) / tps;
+  // balanced partition: every split gets floor(n_tiles / n_splits) tiles, the first n_tiles % n_splits one more (the
+  // LAST split holds the step columns -- masked softmax path, V-row zeroing -- and therefore never the extra tile)
+  const int t_base = n_tiles / n_splits, t_rem = n_tiles - t_base * n_splits;
+  const int n_active = n_tiles < n_splits ? n_tiles : n_splits;
   const bool active = split < n_active;
-  const int tile_lo = split * tps;
-  const int my_tiles = active ? min(n_tiles, tile_lo + tps) - tile_lo : 0;
+  const int tile_lo = split * t_base + (split < t_rem ? split : t_rem);
+  const int my_tiles = active ? t_base + (split < t_rem ? 1 : 0) : 0;
   const int hk = h / (n_heads / n_kv_heads);
   const int HD = n_heads * TC_D;
   long long* tbuf = g_attn_timing ? g_attn_timing + 16ll * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
@@ -127,6 +130,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
   const uint32_t tmem_base = active ? *tmem_slot : 0u;
   const uint32_t tmem_O = tmem_base + 256;
+  // a softmax thread's share of its split's result: 32 fp32 of the unnormalised O row + the row's (max, sum);
+  // they stay in registers across the role join for the split merge at the end of the kernel
+  float ov[32];
+  float m_row = -INFINITY, l_row = 0.f;
 
   if (!active) {
     // an idle split of the cluster: nothing to compute, but it must meet its siblings at the cluster barriers
@@ -243,7 +250,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const float m_new = fmaxf(m_used, mx);
           const float scale = (m_new == -INFINITY) ? 1.f : exp2f((m_used - m_new) * TC_LOG2E);
           l_sum *= scale;
-          float ov[32];
           tmem_ld32(tO, ov);                         // my quarter of the O columns
           tmem_ld_wait();
 #pragma unroll
@@ -268,11 +274,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
           for (int e = 0; e < 8; e += 2) {
             const int i = g * 8 + e;
-            // reference rounding points, two elements per cvt: bf16(bf16(s) * (1/sqrt(d)))
-            const float2 r1 = __bfloat1622float2(__floats2bfloat162_rn(v[i], v[i + 1]));
-            const float2 r2 = __bfloat1622float2(__floats2bfloat162_rn(r1.x * inv_sqrt_d, r1.y * inv_sqrt_d));
-            p[e] = ex2_approx(r2.x * TC_LOG2E - off);
-            p[e + 1] = ex2_approx(r2.y * TC_LOG2E - off);
+            // reference rounding points, two elements per cvt: bf16(bf16(s) * (1/sqrt(d))).  The halves are unpacked
+            // by hand (one shift, one mask): __bfloat1622float2 costs an extra PRMT per pair.
+            const uint32_t u1 = pack2_bf16(v[i], v[i + 1]);
+            const uint32_t u2 = pack2_bf16(__uint_as_float(u1 << 16) * inv_sqrt_d, __uint_as_float(u1 & 0xffff0000u) * inv_sqrt_d);
+            p[e] = ex2_approx(__uint_as_float(u2 << 16) * TC_LOG2E - off);
+            p[e + 1] = ex2_approx(__uint_as_float(u2 & 0xffff0000u) * TC_LOG2E - off);
             ps4[g] += p[e] + p[e + 1];
           }
           uint4 pk;
@@ -288,10 +295,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
           for (int e = 0; e < 8; e += 2) {
             const int i = g * 8 + e;
-            const float2 r1 = __bfloat1622float2(__floats2bfloat162_rn(v[i], v[i + 1]));
-            const float2 r2 = __bfloat1622float2(__floats2bfloat162_rn(r1.x * inv_sqrt_d, r1.y * inv_sqrt_d));
-            p[e] = ((mb >> i) & 1u) ? ex2_approx(r2.x * TC_LOG2E - off) : 0.f;
-            p[e + 1] = ((mb >> (i + 1)) & 1u) ? ex2_approx(r2.y * TC_LOG2E - off) : 0.f;
+            const uint32_t u1 = pack2_bf16(v[i], v[i + 1]);
+            const uint32_t u2 = pack2_bf16(__uint_as_float(u1 << 16) * inv_sqrt_d, __uint_as_float(u1 & 0xffff0000u) * inv_sqrt_d);
+            p[e] = ((mb >> i) & 1u) ? ex2_approx(__uint_as_float(u2 << 16) * TC_LOG2E - off) : 0.f;
+            p[e + 1] = ((mb >> (i + 1)) & 1u) ? ex2_approx(__uint_as_float(u2 & 0xffff0000u) * TC_LOG2E - off) : 0.f;
             ps4[g] += p[e] + p[e + 1];
           }
           uint4 pk;
@@ -322,7 +329,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (j == 1) TC_STAMP(15, 64);
     }
 
-    // ---- epilogue: row sums meet, O (TMEM) -> bf16 output (single split) or fp32 staging in smem (cluster merge)
+    // ---- epilogue: row sums meet; O (TMEM) -> registers.  Single split: normalise and store.  Split-KV: the registers
+    // are pushed to the owner CTA of the row after the role branches join (tail of the kernel).
     mbar_wait(BAR(B_OFINAL), 0);
     tc_fence_after();
     TC_STAMP(TS_OFINAL, 64);
@@ -330,9 +338,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     s_xsum[q4 * 128 + row_l] = l_sum;
     named_bar_sync(1, TC_SOFTMAX_THREADS);
     l_sum = (s_xsum[row_l] + s_xsum[128 + row_l]) + (s_xsum[256 + row_l] + s_xsum[384 + row_l]);
-    float ov[32];
     tmem_ld32(tO, ov);
     tmem_ld_wait();
+    m_row = m_used;
+    l_row = l_sum;
     if (n_splits == 1) {
       const float inv = l_sum > 0.f ? 1.f / l_sum : 0.f;
       if (row < q_pad) {
@@ -347,12 +356,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           dst[v4] = pk;
         }
       }
-    } else {
-      float* so = reinterpret_cast<float*>(smem + TC_SO_OFFSET) + row_l * TC_SO_STRIDE + q4 * 32;
-#pragma unroll
-      for (int v4 = 0; v4 < 8; ++v4)
-        reinterpret_cast<float4*>(so)[v4] = make_float4(ov[v4 * 4], ov[v4 * 4 + 1], ov[v4 * 4 + 2], ov[v4 * 4 + 3]);
-      if (q4 == 0) reinterpret_cast<float2*>(smem + TC_SML_OFFSET)[row_l] = make_float2(m_used, l_sum);
     }
     tc_fence_before();
   }
@@ -368,101 +371,72 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   TC_STAMP(TS_STAGED, 0);
   if (n_splits == 1) { TC_STAMP(TS_END, 0); return; }
 
-  // ---- split merge across the cluster through distributed shared memory ----
-  // Every CTA staged its unnormalised O (fp32) and (m, l) per row in its own smem.  After the cluster barrier,
-  // CTA c merges 1/n_active of the rows: weights w_s = 2^(m_s - m) / sum_s l_s 2^(m_s - m), out = sum_s w_s O_s.
+  // ---- split merge across the cluster: PUSH through distributed shared memory ----
+  // Row r of the tile is owned by CTA r / per (per = ceil(128 / n_active)).  Every softmax thread holds 32 fp32 of
+  // its split's unnormalised O row (and the row's (m, l)) in registers: threads whose row belongs to a sibling store
+  // them straight into the owner's shared memory (st.shared::cluster, fire and forget -- no local staging, no
+  // dependent remote loads), threads of owned rows keep theirs.  Barrier 1: every CTA is done with its K/V stages
+  // (the slots alias them).  Barrier 2: the pushes have landed.  Then the owner threads combine their registers with
+  // the n_active-1 slots from LOCAL shared memory:  w_s = 2^(m_s - m),  out = sum_s w_s O_s / sum_s w_s l_s.
   cluster_arrive();
   cluster_wait();
   TC_STAMP(TS_CLUSTER, 0);
-  if (active) {
-    const int per = (TC_BM + n_active - 1) / n_active;
-    const int row_lo = split * per;
-    const int n_rows = max(0, min(TC_BM, row_lo + per) - row_lo);
-    const uint32_t sml_a = sQ_a + TC_SML_OFFSET, so_a = sQ_a + TC_SO_OFFSET;
-    // item = (row, 4 columns): consecutive lanes read consecutive float4 of one staged row (conflict-free in the
-    // sibling's shared memory, one 512-byte row per warp instruction).
-    const int n_items = n_rows * (TC_D / 4);
-    if (n_active <= 4) {
-      // common case: a thread issues every load of its (up to 3) items before using any of them
-      for (int base = 0; base < n_items; base += 3 * TC_THREADS) {
-        float2 ml[3][4];
-        float4 v[3][4];
+  const int per = (TC_BM + n_active - 1) / n_active;
+  int dest = -1, r_in = 0;
+  if (active && warp >= 2) {
+    const int row_l = (warp & 3) * 32 + lane;
+    const int q4 = (warp - 2) >> 2;
+    dest = row_l / per;
+    r_in = row_l - dest * per;
+    if (dest != split) {
+      const int slot = split < dest ? split : split - 1;
+      const uint32_t o_a = dsmem_addr(sQ_a + TC_SO_OFFSET + (uint32_t)(((slot * per + r_in) * TC_SO_STRIDE + q4 * 32) * 4), dest);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int idx = base + k * TC_THREADS + threadIdx.x;
-          const bool ok = idx < n_items;
-          const int r = ok ? idx / (TC_D / 4) : 0, c4 = idx % (TC_D / 4);
-          const uint32_t ml_a = sml_a + (uint32_t)(row_lo + r) * 8u;
-          const uint32_t o_a = so_a + (uint32_t)((row_lo + r) * TC_SO_STRIDE + c4 * 4) * 4u;
+      for (int v4 = 0; v4 < 8; ++v4) st_dsmem_f4(o_a + v4 * 16, ov[v4 * 4], ov[v4 * 4 + 1], ov[v4 * 4 + 2], ov[v4 * 4 + 3]);
+      if (q4 == 0) st_dsmem_f2(dsmem_addr(sQ_a + TC_SML_OFFSET + (uint32_t)((slot * per + r_in) * 8), dest), m_row, l_row);
+    }
+  }
+  cluster_arrive();
+  cluster_wait();
+  TC_STAMP(TS_MERGED, 0);
+  if (active && warp >= 2 && dest == split) {
+    const int row_l = (warp & 3) * 32 + lane;
+    const int q4 = (warp - 2) >> 2;
+    const int row = mt * TC_BM + row_l;
+    const float2* sml = reinterpret_cast<const float2*>(smem + TC_SML_OFFSET);
+    const float* so = reinterpret_cast<const float*>(smem + TC_SO_OFFSET);
+    float mmax = m_row;
+    for (int k = 0; k < n_active - 1; ++k) mmax = fmaxf(mmax, sml[k * per + r_in].x);
+    float wgt = (m_row == -INFINITY) ? 0.f : exp2f((m_row - mmax) * TC_LOG2E);
+    float lsum = l_row * wgt;
 #pragma unroll
-          for (int sp = 0; sp < 4; ++sp) {
-            const bool live = ok && sp < n_active;
-            ml[k][sp] = live ? ld_dsmem_f2(dsmem_addr(ml_a, sp)) : make_float2(-INFINITY, 0.f);
-            v[k][sp] = live ? ld_dsmem_f4(dsmem_addr(o_a, sp)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
+    for (int i = 0; i < 32; ++i) ov[i] *= wgt;
+    for (int k = 0; k < n_active - 1; ++k) {
+      const float2 ml = sml[k * per + r_in];
+      wgt = (ml.x == -INFINITY) ? 0.f : exp2f((ml.x - mmax) * TC_LOG2E);
+      lsum += ml.y * wgt;
+      const float4* src = reinterpret_cast<const float4*>(so + (k * per + r_in) * TC_SO_STRIDE + q4 * 32);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int idx = base + k * TC_THREADS + threadIdx.x;
-          if (idx >= n_items) continue;
-          const int r = idx / (TC_D / 4), c4 = idx % (TC_D / 4);
-          const float mmax = fmaxf(fmaxf(ml[k][0].x, ml[k][1].x), fmaxf(ml[k][2].x, ml[k][3].x));
-          float lsum = 0.f;
-          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int sp = 0; sp < 4; ++sp) {
-            const float wgt = (ml[k][sp].x == -INFINITY) ? 0.f : exp2f((ml[k][sp].x - mmax) * TC_LOG2E);
-            lsum += ml[k][sp].y * wgt;
-            a.x += v[k][sp].x * wgt; a.y += v[k][sp].y * wgt; a.z += v[k][sp].z * wgt; a.w += v[k][sp].w * wgt;
-          }
-          const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
-          const int row = mt * TC_BM + row_lo + r;
-          if (row < q_pad) {
-            uint2 pk;
-            pk.x = pack2_bf16(a.x * inv, a.y * inv);
-            pk.y = pack2_bf16(a.z * inv, a.w * inv);
-            *reinterpret_cast<uint2*>(out + (long long)row * HD + h * TC_D + c4 * 4) = pk;
-          }
-        }
+      for (int v4 = 0; v4 < 8; ++v4) {
+        const float4 x = src[v4];
+        ov[v4 * 4] += x.x * wgt; ov[v4 * 4 + 1] += x.y * wgt; ov[v4 * 4 + 2] += x.z * wgt; ov[v4 * 4 + 3] += x.w * wgt;
       }
-    } else {
-      for (int idx = threadIdx.x; idx < n_items; idx += TC_THREADS) {
-        const int r = idx / (TC_D / 4), c4 = idx % (TC_D / 4);
-        const uint32_t ml_a = sml_a + (uint32_t)(row_lo + r) * 8u;
-        const uint32_t o_a = so_a + (uint32_t)((row_lo + r) * TC_SO_STRIDE + c4 * 4) * 4u;
-        float2 ml[8];
-        float4 v[8];
+    }
+    const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
+    if (row < q_pad) {
+      uint4* dst = reinterpret_cast<uint4*>(out + (long long)row * HD + h * TC_D + q4 * 32);
 #pragma unroll
-        for (int sp = 0; sp < 8; ++sp) {
-          const bool live = sp < n_active;
-          ml[sp] = live ? ld_dsmem_f2(dsmem_addr(ml_a, sp)) : make_float2(-INFINITY, 0.f);
-          v[sp] = live ? ld_dsmem_f4(dsmem_addr(o_a, sp)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        float mmax = -INFINITY;
-#pragma unroll
-        for (int sp = 0; sp < 8; ++sp) mmax = fmaxf(mmax, ml[sp].x);
-        float lsum = 0.f;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int sp = 0; sp < 8; ++sp) {
-          const float wgt = (ml[sp].x == -INFINITY) ? 0.f : exp2f((ml[sp].x - mmax) * TC_LOG2E);
-          lsum += ml[sp].y * wgt;
-          a.x += v[sp].x * wgt; a.y += v[sp].y * wgt; a.z += v[sp].z * wgt; a.w += v[sp].w * wgt;
-        }
-        const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
-        const int row = mt * TC_BM + row_lo + r;
-        if (row < q_pad) {
-          uint2 pk;
-          pk.x = pack2_bf16(a.x * inv, a.y * inv);
-          pk.y = pack2_bf16(a.z * inv, a.w * inv);
-          *reinterpret_cast<uint2*>(out + (long long)row * HD + h * TC_D + c4 * 4) = pk;
-        }
+      for (int v4 = 0; v4 < 4; ++v4) {
+        uint4 pk;
+        pk.x = pack2_bf16(ov[v4 * 8 + 0] * inv, ov[v4 * 8 + 1] * inv);
+        pk.y = pack2_bf16(ov[v4 * 8 + 2] * inv, ov[v4 * 8 + 3] * inv);
+        pk.z = pack2_bf16(ov[v4 * 8 + 4] * inv, ov[v4 * 8 + 5] * inv);
+        pk.w = pack2_bf16(ov[v4 * 8 + 6] * inv, ov[v4 * 8 + 7] * inv);
+        dst[v4] = pk;
       }
     }
   }
-  TC_STAMP(TS_MERGED, 0);
-  cluster_arrive();      // nobody may exit while a sibling still reads its shared memory
-  cluster_wait();
+  // nobody reads a sibling's shared memory after barrier 2: a CTA may exit as soon as it has stored its rows
   TC_STAMP(TS_END, 0);
 }
 

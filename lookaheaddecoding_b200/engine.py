@@ -52,8 +52,24 @@ class LookaheadEngine:
     def __init__(self, model, window_size: int, level: int, guess_set_size: int,
                  pool_from_prompt: bool = False, max_total_len: int = 4096, attn_impl: int = 0,
                  attn_splits: Optional[int] = None, use_cuda_graph: bool = True, debug: bool = False,
-                 dist_workers: int = 1, rank: int = 0, process_group=None, pipeline_host: bool = True):
+                 dist_workers: int = 1, rank: int = 0, process_group=None, pipeline_host: bool = True,
+                 l2_prefetch: Optional[bool] = None, prefetch_mb: Optional[Sequence[float]] = None,
+                 prefetch_ctas: int = 32, prefetch_chunk: int = 32768):
         self.lib = _cabi.load()
+        # L2 weight prefetch on a side branch of the step graph (see _prefetch): MB of the NEXT projection's weights
+        # requested while [rmsnorm | rope+attention | rmsnorm | swiglu | final norm] run.  MEASURED NEGATIVE on B200
+        # (profiles/r02_l2_prefetch_ab.md: 254 -> 232 tokens/s with 32/110/32/36/36 MB, 246 with the attention window
+        # only; a projection reading L2-resident weights is only 10-15 % faster than from HBM): OFF unless asked for.
+        import os as _os
+        if l2_prefetch is None:
+            l2_prefetch = _os.environ.get("LADE_L2_PREFETCH", "0") == "1"
+        self.l2_prefetch = bool(l2_prefetch)
+        env_mb = _os.environ.get("LADE_PREFETCH_MB")
+        if prefetch_mb is None and env_mb:
+            prefetch_mb = [float(x) for x in env_mb.split(",")]
+        self.prefetch_mb = tuple(prefetch_mb) if prefetch_mb is not None else (32.0, 110.0, 32.0, 36.0, 36.0)
+        self.prefetch_ctas, self.prefetch_chunk = int(prefetch_ctas), int(prefetch_chunk)
+        self._pf_stream = None
         self.pipeline_host = bool(pipeline_host)
         cfg = model.config
         p0 = next(model.parameters())
@@ -272,10 +288,13 @@ class LookaheadEngine:
         qb = self.qb if rows == self.rows_cap else self.qb.view(-1)[: self.nh * rows * self.D].view(self.nh, rows, self.D)
         delta = None
         kv_bound = self.kv_capacity
+        pf = self.prefetch_mb if (self.l2_prefetch and not prefill) else (0, 0, 0, 0, 0)
         for l in range(L):
+            n += self._prefetch([(self.w_qkv[l], 0)], pf[0])                              # beside rmsnorm
             check(lib.lade_rmsnorm(stream, _ptr(h), _ptr(delta), _ptr(self.ln1[l]), _ptr(h) if delta is not None else 0,
                                    _ptr(xn), rows, self.H, self.eps), "lade_rmsnorm"); n += 1
             torch.mm(xn, self.w_qkv[l].t(), out=qkv)
+            n += self._prefetch([(self.w_o[l], 0), (self.w_gu[l], 0)], pf[1])              # beside rope + attention
             kc, vc = self.kv[l, 0], self.kv[l, 1]
             check(lib.lade_rope_append(stream, _ptr(qkv), _ptr(self.cos), _ptr(self.sin), _ptr(self.pos), _ptr(self.meta),
                                        _ptr(qb), _ptr(kc), _ptr(vc), rows, rows, self.nh, self.nkv, self.D,
@@ -284,14 +303,19 @@ class LookaheadEngine:
                                     _ptr(self.meta), _ptr(self.attn_scratch), rows, self.nh, self.nkv, self.D,
                                     self.kv_capacity, kv_bound, self.attn_splits, self.attn_impl), "lade_attn_fwd"); n += 1
             torch.mm(attn_out, self.w_o[l].t(), out=o_buf)
+            gu_done = max(0, int(pf[1] * 1e6) - self.w_o[l].numel() * 2) & ~15
+            n += self._prefetch([(self.w_gu[l], gu_done)], pf[2])                          # beside rmsnorm
             check(lib.lade_rmsnorm(stream, _ptr(h), _ptr(o_buf), _ptr(self.ln2[l]), _ptr(h), _ptr(xn), rows, self.H,
                                    self.eps), "lade_rmsnorm"); n += 1
             torch.mm(xn, self.w_gu[l].t(), out=gu)
+            n += self._prefetch([(self.w_down[l], 0)], pf[3])                              # beside swiglu
             check(lib.lade_swiglu(stream, _ptr(gu), _ptr(act), rows, self.I), "lade_swiglu"); n += 1
             torch.mm(act, self.w_down[l].t(), out=d_buf)
             delta = d_buf
+        n += self._prefetch([(self.lm_head, 0)], pf[4])                                    # beside the final norm
         check(lib.lade_rmsnorm_gather(stream, _ptr(h), _ptr(delta), _ptr(self.norm_w), _ptr(self.lm_rows),
                                       _ptr(self.xn_lm), self.lm_cap, self.H, self.eps), "lade_rmsnorm_gather"); n += 1
+        self._prefetch_join()
         torch.mm(self.xn_lm, self.lm_head.t(), out=self.logits)
         check(lib.lade_argmax_rows(stream, _ptr(self.logits), self.lm_cap, self.V, self.V, _ptr(self.am)),
               "lade_argmax_rows"); n += 1
@@ -303,6 +327,37 @@ class LookaheadEngine:
             check(lib.lade_lp_verify(self._ctx, stream, _ptr(self.am), _ptr(self.meta), _ptr(self.lp_send)),
                   "lade_lp_verify"); n += 1
         return n
+
+    def _prefetch(self, pieces, budget_mb: float) -> int:
+        """Fork: queue an L2 prefetch of up to `budget_mb` MB of `pieces` ([(tensor, byte offset)] in consumption
+        order) on the side stream, ordered after everything queued on the current stream so far, so that it runs
+        BESIDE the kernels queued next (norm / RoPE / attention / SwiGLU: HBM idle).  Returns #kernels launched."""
+        if not self.l2_prefetch or budget_mb <= 0:
+            return 0
+        cur = torch.cuda.current_stream(self.dev)
+        if self._pf_stream is None:
+            self._pf_stream = torch.cuda.Stream(device=self.dev)
+        self._pf_stream.wait_stream(cur)
+        left = int(budget_mb * 1e6)
+        n = 0
+        for t, off in pieces:
+            nbytes = (min(left, t.numel() * t.element_size() - off)) & ~15
+            if nbytes <= 0:
+                continue
+            check(self.lib.lade_l2_prefetch(self._pf_stream.cuda_stream, t.data_ptr() + off, nbytes, self.prefetch_ctas,
+                                            self.prefetch_chunk), "lade_l2_prefetch")
+            n += 1
+            left -= nbytes
+            if left <= 0:
+                break
+        self._pf_dirty = True
+        return n
+
+    def _prefetch_join(self) -> None:
+        """Join the side branch back (a captured graph must end on its origin stream)."""
+        if self._pf_stream is not None and getattr(self, "_pf_dirty", False):
+            torch.cuda.current_stream(self.dev).wait_stream(self._pf_stream)
+            self._pf_dirty = False
 
     def _launch_commit(self, stream: int) -> int:
         """State update of the step.  Single GPU: fused verify+accept+update, then KV compaction.

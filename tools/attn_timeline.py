@@ -34,7 +34,7 @@ for kv, ns in [(1024, 4), (3072, 4)]:
     _cabi.check(lib.lade_debug_attn_timing(0))
     t = tb.cpu().numpy().reshape(-1, 16).astype(np.float64)
     t = t[t[:, 0] > 0]
-    names = ["start", "kfull0", "sfull0", "ofinal", "staged", "cluster", "merged", "end", "t1_begin", "t1_sfull", "t1_ld", "t1_max", "t1_bar", "t1_exp", "t1_fence", "t1_arrive"]
+    names = ["start", "kfull0", "sfull0", "ofinal", "compute_done", "barrier1", "pushed_barrier2", "end", "t1_begin", "t1_sfull", "t1_ld", "t1_max", "t1_bar", "t1_exp", "t1_fence", "t1_arrive"]
     rel = (t - t[:, :1]) / 1.965e3     # us at 1965 MHz
     print(json.dumps({"kv": kv, "splits": ns, "ctas": int(len(t)),
                       "median_us_since_start": {n: round(float(np.median(rel[:, i])), 2) for i, n in enumerate(names)},
