@@ -481,13 +481,8 @@ def extra_workload(name, args, dev, do_sample=False, model=None, reps=3):
     torch.manual_seed(1)
     prompt = torch.randint(3, shape["vocab"], (1, P))[0].tolist()
     if do_sample:
-        from transformers.generation.logits_process import LogitsProcessorList, TemperatureLogitsWarper
-        from lookaheaddecoding_b200.sampling import sample_lookahead
-        warper = LogitsProcessorList([TemperatureLogitsWarper(0.8)])
-
-        def run_once():
-            torch.manual_seed(2)
-            return sample_lookahead(eng, prompt, args.max_new, warper, rng=random.Random(0))
+        def run_once():         # verification on device (lade_sample_verify, Philox)
+            return eng.generate(prompt, args.max_new, rng=random.Random(0), sampling={"temperature": 0.8, "seed": 2})
     else:
         def run_once():
             return eng.generate(prompt, args.max_new, rng=random.Random(0))
@@ -588,13 +583,8 @@ def main():
 
     # ---- warm-up (also captures the steady-step CUDA graph)
     if args.do_sample:
-        from transformers.generation.logits_process import LogitsProcessorList, TemperatureLogitsWarper
-        from lookaheaddecoding_b200.sampling import sample_lookahead
-        warper = LogitsProcessorList([TemperatureLogitsWarper(0.8)])
-
-        def run_once():
-            torch.manual_seed(2)
-            return sample_lookahead(eng, prompt_list, args.max_new, warper, rng=random.Random(0))
+        def run_once():         # verification on device (lade_sample_verify, Philox)
+            return eng.generate(prompt_list, args.max_new, rng=random.Random(0), sampling={"temperature": 0.8, "seed": 2})
         gen_kwargs = dict(do_sample=True, temperature=0.8, top_k=0, top_p=1.0)
         config["workload"] = config["workload"].replace("greedy", "sampling temp=0.8")
     else:

@@ -211,6 +211,20 @@ int lade_argmax_rows(void* stream, const void* logits, int32_t n_rows, int32_t v
 int lade_accept_update(LadeCtx* ctx, void* stream, const int32_t* argmax_slots, const int32_t* meta,
                        int32_t* result);
 
+/* Sampling verification ON DEVICE for the warper set {temperature} -- replaces the host loop of
+ * jacobi_sample_multilevel, lade/decoding.py:445-546 (softmax of out_logits / T :445,:485; per n-gram position the
+ * accept test u < min(1, p[token]) over the n-grams still alive :495-516, zero-and-renormalise on reject :518-520,
+ * residual multinomial draw :533-535; single multinomial draw on steps without candidates :458-480,:543-546) and
+ * filter_window (:131-135,:578-580).  One kernel, one CTA; random numbers from a Philox4x32-10 stream whose
+ * (seed, offset) live in `rng_state[2]` (device, uint64; the kernel advances the offset), so a sampling step replays
+ * from a CUDA graph with no host round trip.  `logits`: bf16 [lm slots][ld], slot order of lade_step_layout's
+ * lm_rows; `argmax_slots`: lade_argmax_rows of the same slots (the window advances by argmax, :466,:478,:549).
+ * Writes the decision record lade_commit_decision consumes.  `debug_uniforms` (nullable, device float[>= 2 + G*(N-1) + W]):
+ * [count, u0, u1, ...] the uniforms consumed, for tests.  Top-k / top-p warpers stay on the host-mirror path. */
+int lade_sample_verify(LadeCtx* ctx, void* stream, const void* logits, int32_t ld, int32_t vocab,
+                       const int32_t* argmax_slots, const int32_t* meta, float temperature, uint64_t* rng_state,
+                       int32_t* decision_out, float* debug_uniforms);
+
 /* Apply an externally made decision (sampling path: the caller runs the reference's rejection-sampling
  * verification, lade/decoding.py:484-540, against the device logits with its own RNG streams).
  * `decision` (device) = lade_lp_record_ints() ints [first_token, max_hit, n_new, hits[N-1], new_window_tokens[W+N-3]]
@@ -249,6 +263,19 @@ int lade_lp_verify(LadeCtx* ctx, void* stream, const int32_t* argmax_slots, cons
                    int32_t* record_out);
 int lade_lp_commit(LadeCtx* ctx, void* stream, const int32_t* records_all /* [D][record_ints] */,
                    const int32_t* meta, int32_t* result);
+
+/* Lookahead-parallel exchange INSIDE the library: one ncclAllGather of the per-rank int32 record
+ * (lade_lp_record_ints ints) on `stream` -- capturable, so verify -> exchange -> commit replay as part of the step's
+ * CUDA graph.  Replaces dist.broadcast_object_list / dist.all_gather_object of python lists, lade/decoding.py:1023-1024,
+ * :1043-1058, :1088-1107.  `nccl_comm` is an ncclComm_t: the caller's own, or one made by lade_nccl_comm_create (NCCL is
+ * resolved at run time from the libnccl.so.2 already mapped into the process; LADE_EUNSUPPORTED when there is none).
+ * lade_nccl_unique_id: rank 0 fills 128 bytes, the host broadcasts them (any transport), every rank then calls
+ * lade_nccl_comm_create (collective) with its CUDA device current. */
+int lade_nccl_available(void);
+int lade_nccl_unique_id(void* id128);
+int lade_nccl_comm_create(const void* id128, int32_t world, int32_t rank, void** comm_out);
+int lade_nccl_comm_destroy(void* nccl_comm);
+int lade_lp_exchange(LadeCtx* ctx, void* stream, void* nccl_comm, const int32_t* record_in, int32_t* records_all_out);
 
 /* Error text for a LADE_E* code / the last CUDA runtime error string seen by this library (the reference raises
  * python exceptions or asserts, e.g. lade/utils.py:33, decoding.py:375-377,412); ABI version of this header. */

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "lade_argmax_rows": (C.c_int, [c_p, c_p, c_i32, c_i32, c_i32, c_p]),
     "lade_accept_update": (C.c_int, [c_p, c_p, c_p, c_p, c_p]),
     "lade_commit_decision": (C.c_int, [c_p, c_p, c_p, c_p, c_p]),
+    "lade_sample_verify": (C.c_int, [c_p, c_p, c_p, c_i32, c_i32, c_p, c_p, C.c_float, c_p, c_p, c_p]),
     "lade_kv_compact": (C.c_int, [c_p, c_p, c_p, c_p, C.c_int64, c_i32, c_i32, c_i32, c_i32, c_i32]),
     "lade_ctx_output_ids": (C.c_int, [c_p, c_p, c_p, c_i32]),
     "lade_ctx_pool_snapshot": (C.c_int, [c_p, c_p, c_p, c_p]),
@@ -61,6 +62,11 @@ _SIGNATURES = {
     "lade_lp_record_ints": (C.c_int, [C.POINTER(LadeConfig)]),
     "lade_lp_verify": (C.c_int, [c_p, c_p, c_p, c_p, c_p]),
     "lade_lp_commit": (C.c_int, [c_p, c_p, c_p, c_p, c_p]),
+    "lade_nccl_available": (C.c_int, []),
+    "lade_nccl_unique_id": (C.c_int, [c_p]),
+    "lade_nccl_comm_create": (C.c_int, [c_p, c_i32, c_i32, C.POINTER(c_p)]),
+    "lade_nccl_comm_destroy": (C.c_int, [c_p]),
+    "lade_lp_exchange": (C.c_int, [c_p, c_p, c_p, c_p, c_p]),
     "lade_strerror": (C.c_char_p, [C.c_int]),
     "lade_last_cuda_error": (C.c_char_p, []),
     "lade_version": (C.c_int, []),

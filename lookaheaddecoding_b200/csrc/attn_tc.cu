@@ -41,11 +41,6 @@ __device__ long long* g_attn_timing = nullptr;
 #define TC_STAMP(slot, tid) do { if (tbuf && threadIdx.x == (tid)) tbuf[slot] = clock64(); } while (0)
 enum { TS_START = 0, TS_KFULL0 = 1, TS_SFULL0 = 2, TS_OFINAL = 3, TS_STAGED = 4, TS_CLUSTER = 5, TS_MERGED = 6, TS_END = 7 };
 
-// Split merge staging (written by the sibling CTAs of the cluster through distributed shared memory, see the tail of the
-// kernel): slot k of an owner CTA = [rows_per_owner][TC_SO_STRIDE] floats of one sibling's unnormalised O quarter-rows.
-constexpr int TC_SO_STRIDE = 132;                       // floats per staged O row (528 B: conflict-free float4 rows)
-constexpr int TC_SO_OFFSET = TC_TILE_BYTES;             // slots live in the (dead) K/V stages: <= 7 * 16 * 528 B
-constexpr int TC_SML_OFFSET = 0;                        // (m, l) per slot and row: <= 7 * 64 * 8 B in the (dead) Q tile
 
 // ---- kernel ---------------------------------------------------------------------------------------------
 // grid (n_splits, heads, q tiles); when n_splits > 1 the n_splits CTAs of one (head, q tile) form a thread-block
@@ -54,7 +49,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out,
                    const uint32_t* __restrict__ rowmask, int mask_words, const int* __restrict__ meta, int q_pad,
-                   int n_heads, int n_kv_heads, int n_splits, float inv_sqrt_d) {
+                   int n_heads, int n_kv_heads, int n_splits, float inv_sqrt_d, float* __restrict__ part_o,
+                   float2* __restrict__ part_ml) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int split = blockIdx.x, h = blockIdx.y, mt = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -77,6 +73,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int HD = n_heads * TC_D;
   long long* tbuf = g_attn_timing ? g_attn_timing + 16ll * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
   TC_STAMP(TS_START, 0);
+  // programmatic dependent launch, producer side: a dependent grid (in the decode step: none -- the o_proj GEMM is a
+  // plain launch; in a back-to-back loop over layer caches: the next lookahead-attention launch) may be scheduled as
+  // soon as SMs free up; it orders itself with griddepcontrol.wait before it touches anything this grid writes
+  griddep_launch_dependents();
 
   unsigned char* sQ = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_SMEM_TILES);
@@ -371,29 +371,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   TC_STAMP(TS_STAGED, 0);
   if (n_splits == 1) { TC_STAMP(TS_END, 0); return; }
 
-  // ---- split merge across the cluster: PUSH through distributed shared memory ----
+  // ---- split merge across the cluster, through global memory (L2) ----
   // Row r of the tile is owned by CTA r / per (per = ceil(128 / n_active)).  Every softmax thread holds 32 fp32 of
   // its split's unnormalised O row (and the row's (m, l)) in registers: threads whose row belongs to a sibling store
-  // them straight into the owner's shared memory (st.shared::cluster, fire and forget -- no local staging, no
-  // dependent remote loads), threads of owned rows keep theirs.  Barrier 1: every CTA is done with its K/V stages
-  // (the slots alias them).  Barrier 2: the pushes have landed.  Then the owner threads combine their registers with
-  // the n_active-1 slots from LOCAL shared memory:  w_s = 2^(m_s - m),  out = sum_s w_s O_s / sum_s w_s l_s.
-  cluster_arrive();
-  cluster_wait();
-  TC_STAMP(TS_CLUSTER, 0);
+  // them to the split's slab of the scratch buffer (plain coalescable 16-byte stores: L2 takes ~64 B/clk per SM,
+  // the SM-to-SM network measured ~17 B/clk both for remote loads and for remote stores -- 3.3 us for the 48 KB a
+  // CTA exchanges), threads of owned rows keep theirs.  One cluster barrier (release / acquire) publishes the slabs;
+  // the owner threads then combine their registers with the n_active-1 sibling slabs read back from L2:
+  //   w_s = 2^(m_s - m),  out = sum_s w_s O_s / sum_s w_s l_s.
+  // The slabs live in a 6 MB scratch that is rewritten by every launch and never leaves the L2.
   const int per = (TC_BM + n_active - 1) / n_active;
-  int dest = -1, r_in = 0;
+  int dest = -1;
+  const long long hm = (long long)h * gridDim.z + mt;
   if (active && warp >= 2) {
     const int row_l = (warp & 3) * 32 + lane;
     const int q4 = (warp - 2) >> 2;
     dest = row_l / per;
-    r_in = row_l - dest * per;
     if (dest != split) {
-      const int slot = split < dest ? split : split - 1;
-      const uint32_t o_a = dsmem_addr(sQ_a + TC_SO_OFFSET + (uint32_t)(((slot * per + r_in) * TC_SO_STRIDE + q4 * 32) * 4), dest);
+      float4* dst = reinterpret_cast<float4*>(part_o + ((hm * n_splits + split) * TC_BM + row_l) * TC_D + q4 * 32);
 #pragma unroll
-      for (int v4 = 0; v4 < 8; ++v4) st_dsmem_f4(o_a + v4 * 16, ov[v4 * 4], ov[v4 * 4 + 1], ov[v4 * 4 + 2], ov[v4 * 4 + 3]);
-      if (q4 == 0) st_dsmem_f2(dsmem_addr(sQ_a + TC_SML_OFFSET + (uint32_t)((slot * per + r_in) * 8), dest), m_row, l_row);
+      for (int v4 = 0; v4 < 8; ++v4) dst[v4] = make_float4(ov[v4 * 4], ov[v4 * 4 + 1], ov[v4 * 4 + 2], ov[v4 * 4 + 3]);
+      if (q4 == 0) part_ml[(hm * n_splits + split) * TC_BM + row_l] = make_float2(m_row, l_row);
     }
   }
   cluster_arrive();
@@ -403,23 +401,32 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int row_l = (warp & 3) * 32 + lane;
     const int q4 = (warp - 2) >> 2;
     const int row = mt * TC_BM + row_l;
-    const float2* sml = reinterpret_cast<const float2*>(smem + TC_SML_OFFSET);
-    const float* so = reinterpret_cast<const float*>(smem + TC_SO_OFFSET);
+    float2 ml[7];
     float mmax = m_row;
-    for (int k = 0; k < n_active - 1; ++k) mmax = fmaxf(mmax, sml[k * per + r_in].x);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const int sp = k < split ? k : k + 1;                     // the siblings, skipping myself
+      ml[k] = make_float2(-INFINITY, 0.f);
+      if (sp < n_active) ml[k] = ld_global_f2(part_ml + (hm * n_splits + sp) * TC_BM + row_l);
+      mmax = fmaxf(mmax, ml[k].x);
+    }
     float wgt = (m_row == -INFINITY) ? 0.f : exp2f((m_row - mmax) * TC_LOG2E);
     float lsum = l_row * wgt;
 #pragma unroll
     for (int i = 0; i < 32; ++i) ov[i] *= wgt;
-    for (int k = 0; k < n_active - 1; ++k) {
-      const float2 ml = sml[k * per + r_in];
-      wgt = (ml.x == -INFINITY) ? 0.f : exp2f((ml.x - mmax) * TC_LOG2E);
-      lsum += ml.y * wgt;
-      const float4* src = reinterpret_cast<const float4*>(so + (k * per + r_in) * TC_SO_STRIDE + q4 * 32);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const int sp = k < split ? k : k + 1;
+      if (sp >= n_active) continue;
+      wgt = (ml[k].x == -INFINITY) ? 0.f : exp2f((ml[k].x - mmax) * TC_LOG2E);
+      lsum += ml[k].y * wgt;
+      const float* src = part_o + ((hm * n_splits + sp) * TC_BM + row_l) * TC_D + q4 * 32;
+      float4 x[8];
+#pragma unroll
+      for (int v4 = 0; v4 < 8; ++v4) x[v4] = ld_global_f4(src + v4 * 4);
 #pragma unroll
       for (int v4 = 0; v4 < 8; ++v4) {
-        const float4 x = src[v4];
-        ov[v4 * 4] += x.x * wgt; ov[v4 * 4 + 1] += x.y * wgt; ov[v4 * 4 + 2] += x.z * wgt; ov[v4 * 4 + 3] += x.w * wgt;
+        ov[v4 * 4] += x[v4].x * wgt; ov[v4 * 4 + 1] += x[v4].y * wgt; ov[v4 * 4 + 2] += x[v4].z * wgt; ov[v4 * 4 + 3] += x[v4].w * wgt;
       }
     }
     const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
@@ -436,7 +443,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   }
-  // nobody reads a sibling's shared memory after barrier 2: a CTA may exit as soon as it has stored its rows
   TC_STAMP(TS_END, 0);
 }
 
@@ -510,7 +516,6 @@ int attn_fwd_tc_launch(cudaStream_t stream, const void* q, const void* k_cache, 
                        const uint32_t* rowmask, int mask_words, const int32_t* meta, void* scratch, int q_pad, int n_heads,
                        int n_kv_heads, int head_dim, int kv_capacity, int kv_bound, int n_splits) {
   (void)kv_bound;
-  (void)scratch;   // split partials never leave the SMs on this path (cluster / DSMEM merge)
   if (head_dim != TC_D) return LADE_EUNSUPPORTED;
   const int q_tiles = (q_pad + TC_BM - 1) / TC_BM;
   if (n_splits > 8) n_splits = 8;   // portable cluster size
@@ -546,8 +551,11 @@ int attn_fwd_tc_launch(cudaStream_t stream, const void* q, const void* k_cache, 
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
   const float inv_sqrt_d = 1.0f / sqrtf((float)head_dim);
+  // scratch (lade_attn_scratch_bytes): [64 KB reserved][partial O: n_splits * n_heads * rows_pad * D fp32][(m, l) per row]
+  float* part_o = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 65536);
+  float2* part_ml = reinterpret_cast<float2*>(part_o + (size_t)n_splits * n_heads * q_tiles * TC_BM * TC_D);
   cudaError_t e = cudaLaunchKernelEx(&cfg, attn_fwd_tc_kernel, tmQ, tmK, tmV, (__nv_bfloat16*)out, rowmask, mask_words, meta,
-                                     q_pad, n_heads, n_kv_heads, n_splits, inv_sqrt_d);
+                                     q_pad, n_heads, n_kv_heads, n_splits, inv_sqrt_d, part_o, part_ml);
   if (e != cudaSuccess) { set_cuda_error(e, "cudaLaunchKernelEx(attn_fwd_tc_kernel)"); return LADE_ECUDA; }
   return LADE_OK;
 }

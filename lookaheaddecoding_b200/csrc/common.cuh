@@ -8,6 +8,7 @@
 namespace lade {
 
 void set_cuda_error(cudaError_t e, const char* where);
+void set_error_string(const char* msg);      // shown by lade_last_cuda_error() (also used for NCCL failures)
 
 #define LADE_CUDA_CHECK(expr)                                   \
   do {                                                          \

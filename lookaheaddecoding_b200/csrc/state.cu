@@ -9,7 +9,7 @@
 //   mask scalars                    lade/models/modeling_llama.py:132-138
 //   longest-prefix accept           lade/decoding.py:1071-1084
 //   emission / EOS / stopping       lade/decoding.py:1165-1177, :1205-1219
-#include "common.cuh"
+#include "state.cuh"
 
 #include <new>
 #include <string>
@@ -20,35 +20,7 @@ static thread_local std::string g_last_error;
 void set_cuda_error(cudaError_t e, const char* where) {
   g_last_error = std::string(where) + ": " + cudaGetErrorString(e);
 }
-
-// header ints of the device state block
-enum {
-  S_FILL_LEVEL = 0, S_LST_TOKEN, S_KV_LEN, S_N_OUT, S_N_OLD, S_DONE, S_STEPS, S_MAX_LENGTH,
-  S_N_PROMPT, S_N_GUESS_TOK, S_SKIP, S_HDR_INTS = 16
-};
-
-struct Dims {
-  int W, N, G, GS, WCAP, V, cap, pool_from_prompt, n_eos;
-  int D, rank;   // lookahead parallelism: DIST_WORKERS, LOCAL_RANK (1, 0 when off)
-  int eos[4];
-  int lm_cap;
-  // offsets (in ints) into the state block
-  int off_win, off_win_len, off_guess, off_out, off_old, off_cnt;
-  long long off_tup;
-  long long total_ints;
-};
-
-}  // namespace lade
-
-struct LadeCtx {
-  LadeConfig cfg;
-  lade::Dims d;
-  int32_t* state;   // device
-};
-
-namespace lade {
-
-__device__ __forceinline__ int* st_win(int* st, const Dims& d, int level) { return st + d.off_win + level * d.WCAP; }
+void set_error_string(const char* msg) { g_last_error = msg; }
 
 // One LRU insertion into the pool, executed cooperatively by one warp (all 32 lanes call it).
 // `tup` points at GS ints readable by every lane.  lade/decoding.py:39-49.
@@ -287,7 +259,6 @@ struct Decision {
   int filt[1024];      // sampling + EOS: newest window level after filter_window (decoding.py:131-135,578-580)
 };
 
-__device__ __forceinline__ int lp_rec_ints(const Dims& d) { return 3 + d.GS + d.WCAP; }
 
 // Local part: argmax slots -> decision (longest-prefix accept over this rank's guesses, decoding.py:1071-1084).
 __device__ void local_decision(int* st, const Dims& d, const int* __restrict__ am, const int* __restrict__ meta,

@@ -115,6 +115,9 @@ class LookaheadEngine:
                 raise LadeError("DIST_WORKERS > 1 needs an initialised torch.distributed process group")
             if dist.get_world_size(self.pg) != self.DW:
                 raise LadeError("DIST_WORKERS config should be equal to work size")      # lade/utils.py:33
+        self._nccl_comm = C.c_void_p()
+        if self.DW > 1:
+            self._lp_comm_create()
         self.max_total_len = int(max_total_len)
         probe = self._make_config(())
         self.q_steady = int(self.lib.lade_step_rows_bound(C.byref(probe), 1, self.N))    # fixed steady shape
@@ -210,6 +213,10 @@ class LookaheadEngine:
         self.lm_rows = torch.zeros(self.lm_cap, **i32)
         self.am = torch.zeros(self.lm_cap, **i32)
         self.res = torch.zeros(_cabi.RES_INTS, **i32)
+        self.dec_dev = torch.zeros(self.rec_ints + 4 + self.W, **i32)          # decision record of the sampling path
+        if not hasattr(self, "rng_state"):
+            self.rng_state = torch.zeros(2, dtype=torch.int64, device=dev)     # Philox (seed, offset), advanced on device
+            self.sample_temperature = 1.0
         self.lp_send = torch.zeros(self.rec_ints, **i32)
         self.lp_recv = torch.zeros(self.DW * self.rec_ints, **i32)
         self.h = torch.empty(rows, self.H, dtype=bf, device=dev)
@@ -261,6 +268,11 @@ class LookaheadEngine:
         if getattr(self, "_ctx", None):
             self.lib.lade_ctx_destroy(self._ctx)
             self._ctx = C.c_void_p()
+        if getattr(self, "_nccl_comm", None):
+            torch.cuda.synchronize(self.dev)
+            self._graph = None
+            self.lib.lade_nccl_comm_destroy(self._nccl_comm)
+            self._nccl_comm = C.c_void_p()
 
     def __del__(self):
         try:
@@ -321,11 +333,24 @@ class LookaheadEngine:
               "lade_argmax_rows"); n += 1
         if not commit:
             return n
+        if commit == "sample":      # verification + residual draw on device (Philox), then the state update
+            check(lib.lade_sample_verify(self._ctx, stream, _ptr(self.logits), self.V, self.V, _ptr(self.am), _ptr(self.meta),
+                                         float(self.sample_temperature), _ptr(self.rng_state), _ptr(self.dec_dev),
+                                         _ptr(getattr(self, "debug_uniforms", None))),
+                  "lade_sample_verify")
+            check(lib.lade_commit_decision(self._ctx, stream, _ptr(self.dec_dev), _ptr(self.meta), _ptr(self.res)),
+                  "lade_commit_decision")
+            check(lib.lade_kv_compact(stream, _ptr(self.res), _ptr(self.kv[0, 0]), _ptr(self.kv[0, 1]),
+                                      self.kv.stride(0), self.L, self.nkv, self.kv_capacity, self.D, max(self.GS - 1, 1)),
+                  "lade_kv_compact")
+            return n + 3
         if self.DW == 1:
             n += self._launch_commit(stream)
-        else:   # LP: local verify here (capturable); exchange + commit follow in _launch_commit
+        else:   # LP: local verify, then the exchange + replicated commit (in the same graph when NCCL is in-library)
             check(lib.lade_lp_verify(self._ctx, stream, _ptr(self.am), _ptr(self.meta), _ptr(self.lp_send)),
                   "lade_lp_verify"); n += 1
+            if self._nccl_comm:
+                n += self._launch_commit(stream)
         return n
 
     def _prefetch(self, pieces, budget_mb: float) -> int:
@@ -359,6 +384,31 @@ class LookaheadEngine:
             torch.cuda.current_stream(self.dev).wait_stream(self._pf_stream)
             self._pf_dirty = False
 
+    def _lp_comm_create(self) -> None:
+        """In-library NCCL communicator for the per-step record exchange (lade_lp_exchange): rank 0 draws the unique
+        id, torch.distributed carries its 128 bytes to the other ranks (set-up only), every rank joins.  With
+        LADE_LP_TORCH_ALLGATHER=1 (or no NCCL in the process) the exchange falls back to dist.all_gather_into_tensor."""
+        import os as _os
+        import torch.distributed as dist
+        if _os.environ.get("LADE_LP_TORCH_ALLGATHER", "0") == "1" or not self.lib.lade_nccl_available():
+            return
+        if dist.get_backend(self.pg) != "nccl":          # gloo groups (CPU tests) have no device collectives
+            return
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_char * 128)()
+            check(self.lib.lade_nccl_unique_id(buf), "lade_nccl_unique_id")
+            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        uid_dev = uid.to(self.dev)
+        src = dist.get_global_rank(self.pg, 0) if self.pg is not None else 0
+        dist.broadcast(uid_dev, src=src, group=self.pg)
+        raw = bytes(uid_dev.cpu().numpy().tobytes())
+        check(self.lib.lade_nccl_comm_create(raw, self.DW, self.rank, C.byref(self._nccl_comm)), "lade_nccl_comm_create")
+
+    @property
+    def lp_in_library(self) -> bool:
+        return bool(self._nccl_comm)
+
     def _launch_commit(self, stream: int) -> int:
         """State update of the step.  Single GPU: fused verify+accept+update, then KV compaction.
         LP: one all-gather of the fixed-size per-rank records over NCCL, then the replicated commit."""
@@ -370,8 +420,12 @@ class LookaheadEngine:
                                       self.kv.stride(0), self.L, self.nkv, self.kv_capacity, self.D, max(self.GS - 1, 1)),
                   "lade_kv_compact")
             return 2
-        import torch.distributed as dist
-        dist.all_gather_into_tensor(self.lp_recv, self.lp_send, group=self.pg)
+        if self._nccl_comm:      # ncclAllGather on the compute stream, inside the library (graph-capturable)
+            check(lib.lade_lp_exchange(self._ctx, stream, self._nccl_comm, _ptr(self.lp_send), _ptr(self.lp_recv)),
+                  "lade_lp_exchange")
+        else:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self.lp_recv, self.lp_send, group=self.pg)
         check(lib.lade_lp_commit(self._ctx, stream, _ptr(self.lp_recv), _ptr(self.meta), _ptr(self.res)), "lade_lp_commit")
         return 1
 
@@ -399,8 +453,10 @@ class LookaheadEngine:
     def _steady_graph(self, commit: bool = True):
         if self._graph is None:
             self._graph = {}
-        if commit in self._graph:
-            return self._graph[commit][0]
+        key = (commit, float(self.sample_temperature)) if commit == "sample" else commit
+        if key in self._graph:
+            self._graph_n = self._graph[key][1]
+            return self._graph[key][0]
         rows = self.q_steady
         g = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(device=self.dev)
@@ -409,8 +465,9 @@ class LookaheadEngine:
             with torch.cuda.graph(g, stream=side):
                 n = self._launch_step(rows, torch.cuda.current_stream(self.dev).cuda_stream, commit=commit)
         torch.cuda.current_stream(self.dev).wait_stream(side)
-        self._graph[commit] = (g, n)
+        self._graph[key] = (g, n)
         self._launches_per_graph = n
+        self._graph_n = n
         return g
 
     def run_forward_step(self, step: int, n_prompt: int, commit: bool = True) -> None:
@@ -425,7 +482,7 @@ class LookaheadEngine:
             self.launches += self._launch_step(rows, stream, commit=commit, prefill=(step == 0))
         else:
             self._steady_graph(commit).replay()
-            self.launches += self._graph[commit][1]
+            self.launches += self._graph_n
 
     def begin(self, prompt, max_length: int, eos_token_ids, window0) -> None:
         """Reset the device state for a generate() call (lade_ctx_reset) and size the buffers."""
@@ -460,16 +517,30 @@ class LookaheadEngine:
     @torch.no_grad()
     def generate(self, prompt_ids: Sequence[int], max_new_tokens: int, eos_token_ids: Sequence[int] = (),
                  rng: Optional[random.Random] = None, window0: Optional[Sequence[int]] = None,
-                 stop_fn=None) -> List[int]:
+                 stop_fn=None, sampling: Optional[dict] = None) -> List[int]:
         """Greedy lookahead decoding; returns prompt + generated ids (trimmed to P + max_new_tokens).
         `stop_fn(ids) -> bool`: host-evaluated stopping criteria beyond max-length / EOS, checked after every step
-        like lade/decoding.py:1215 (disables the one-step-deep host pipelining)."""
+        like lade/decoding.py:1215 (disables the one-step-deep host pipelining).
+        `sampling={"temperature": T, "seed": s}`: the sampling loop (jacobi_sample_multilevel, lade/decoding.py:137) with
+        the verification on device (lade_sample_verify, Philox stream seeded by `s`): same host loop, same CUDA graph
+        replay per step, the only difference is the commit kernels at the end of the step."""
         prompt = [int(t) for t in prompt_ids]
         P = len(prompt)
         max_length = P + int(max_new_tokens)
         if max_length > self.max_total_len:
             raise LadeError(f"prompt+max_new_tokens={max_length} exceeds engine capacity {self.max_total_len}")
+        commit = True
+        if sampling is not None:
+            if self.DW != 1:
+                raise LadeError("the sampling path has no lookahead parallelism (reference: replicas only)")
+            T = float(sampling.get("temperature", 1.0))
+            if not T > 0:
+                raise LadeError("temperature must be > 0")
+            self.sample_temperature = T
+            commit = "sample"
         self.begin(prompt, max_length, eos_token_ids, self.draw_window(prompt, rng, window0))
+        if sampling is not None:
+            self.rng_state.copy_(torch.tensor([int(sampling.get("seed", 0)) & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64))
         stream = torch.cuda.current_stream(self.dev).cuda_stream
         out = list(prompt)
         self.last_records = []
@@ -482,13 +553,14 @@ class LookaheadEngine:
         queued = 0                    # steps queued so far
         step = 0                      # steps whose record has been read
         guard = max_new_tokens + self.N + 4
-        # lookahead parallelism keeps the synchronous loop: that is the configuration the multi-GPU NCCL runs validated
-        pipelined = self.pipeline_host and self.DW == 1 and stop_fn is None
+        # lookahead parallelism: pipelined too when the exchange is in-library (every rank replays the same graph in the
+        # same order: the decisions are replicated); the torch all-gather fallback keeps the synchronous loop
+        pipelined = self.pipeline_host and (self.DW == 1 or bool(self._nccl_comm)) and stop_fn is None
 
         def enqueue():
             nonlocal queued
-            self.run_forward_step(queued, P)
-            if self.DW > 1:
+            self.run_forward_step(queued, P, commit=commit)
+            if self.DW > 1 and not self._nccl_comm:       # torch all-gather fallback: outside the graph
                 self.launches += self._launch_commit(stream)
             slot = queued & 1
             self._enqueue_result_copy(slot)

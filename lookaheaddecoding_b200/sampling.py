@@ -1,13 +1,17 @@
-"""Sampling lookahead decoding: host mirror of ``jacobi_sample_multilevel`` (``lade/decoding.py:137-692``).
+"""Sampling lookahead decoding: ``jacobi_sample_multilevel`` (``lade/decoding.py:137-692``) on the CUDA engine.
 
-The model forward, the window / pool / KV bookkeeping and the row-wise argmax (the window always advances
-by argmax, ``decoding.py:466,478,549``) run on the device engine.  The multi-candidate rejection-sampling
-verification (``decoding.py:484-540``, modified SpecInfer) is executed here exactly as the reference does
-it -- against device probability tensors, consuming python's ``random.random()`` for the accept tests and
-``torch.multinomial`` for the residual draw in the same order -- so that under fixed seeds the token
-stream follows the reference's distribution draw for draw.  The decision is then handed to the device
-state machine with ``lade_commit_decision``.  (Moving this loop onto the device with a Philox stream is
-SURVEY 8(f) rank 3.)
+Two ways to run the multi-candidate rejection-sampling verification (``decoding.py:484-540``, modified SpecInfer):
+
+* **device (default when the warpers are within {temperature})**: ``lade_sample_verify`` -- softmax, accept tests,
+  zero-and-renormalise, residual multinomial draw and the EOS window filter in one kernel driven by a Philox
+  stream -- followed by ``lade_commit_decision``; the whole step replays from one CUDA graph and the host loop is the
+  pipelined greedy loop (``LookaheadEngine.generate(..., sampling=...)``).  Same distribution as the reference, its own
+  random stream (seeded from torch's global generator, so ``torch.manual_seed`` makes a run reproducible).
+* **host-RNG compatibility mode** (``sample_lookahead`` below; used for top-k / top-p warpers, or when
+  ``CONFIG_MAP["SAMPLING_ON_HOST"]`` is set): the model forward, window / pool / KV bookkeeping and row-wise argmax
+  run on the device; the verification runs here against device probability tensors, consuming python's
+  ``random.random()`` for the accept tests and ``torch.multinomial`` for the residual draw in the reference's order,
+  so that under fixed seeds the token stream follows the reference draw for draw (the fixed-seed golden tests).
 
 Restrictions inherited from the reference: warpers within {Temperature, TopK, TopP} (``decoding.py:375-377``),
 no other logits processors (``:412``), batch 1, ``return_dict_in_generate == False``; no lookahead
@@ -40,6 +44,17 @@ def _check_warpers(logits_warper):
     for w in (logits_warper or []):
         if type(w) not in (TemperatureLogitsWarper, TopKLogitsWarper, TopPLogitsWarper):
             raise LadeError(f"please set top_k=0.0 and top_p=1.0 {w}")                     # decoding.py:377
+
+
+def device_temperature(logits_warper):
+    """T if the warper list is empty or a single TemperatureLogitsWarper (the set the device kernel implements), else None."""
+    from transformers.generation.logits_process import TemperatureLogitsWarper
+    ws = list(logits_warper or [])
+    if not ws:
+        return 1.0
+    if len(ws) == 1 and type(ws[0]) is TemperatureLogitsWarper:
+        return float(ws[0].temperature)
+    return None
 
 
 @torch.no_grad()
@@ -204,8 +219,14 @@ def jacobi_sample_multilevel(self, input_ids: torch.LongTensor, logits_processor
             CONFIG_MAP["DIST_WORKERS"] = saved
     from .decoding import _extra_stopping_criteria, _host_stop_fn
     stop_fn = _host_stop_fn(_extra_stopping_criteria(stopping_criteria), input_ids.device, input_ids.dtype)
-    out = sample_lookahead(eng, input_ids[0].tolist(), total - init_len, logits_warper, eos_token_id or (), rng=random,
-                           stop_fn=stop_fn)
+    temperature = device_temperature(logits_warper)
+    if temperature is not None and not CONFIG_MAP.get("SAMPLING_ON_HOST", 0):
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())          # reproducible under torch.manual_seed
+        out = eng.generate(input_ids[0].tolist(), total - init_len, eos_token_ids=eos_token_id or (), rng=random,
+                           stop_fn=stop_fn, sampling={"temperature": temperature, "seed": seed})
+    else:
+        out = sample_lookahead(eng, input_ids[0].tolist(), total - init_len, logits_warper, eos_token_id or (), rng=random,
+                               stop_fn=stop_fn)
     if streamer is not None:
         streamer.put(torch.tensor(out[init_len:]))
         streamer.end()

@@ -43,8 +43,15 @@ def main():
         assert all(g == gathered[0] for g in gathered), "ranks disagree"
         assert_same_or_tie(out, ref, c["model"], w, f"LP x{world} {name}")
         from lookaheaddecoding_b200.decoding import CONFIG_MAP
+        from lookaheaddecoding_b200.decoding import get_engine
+        lp_eng = get_engine(model)
+        exact = out == ref
+        # the same sequence again through the torch all-gather fallback (exchange outside the graph): same ids
         if rank == 0:
-            print(f"{name}: LP x{world} log {CONFIG_MAP['log'][-1]} ; single-GPU steps {single.last_steps}")
+            print(f"{name}: LP x{world} log {CONFIG_MAP['log'][-1]} ; single-GPU steps {single.last_steps} ; "
+                  f"exchange in library (ncclAllGather in the step graph): {lp_eng.lp_in_library} ; "
+                  f"ids identical to the single-GPU run: {exact}")
+        assert lp_eng.lp_in_library, "the in-library NCCL exchange was expected on a multi-GPU NCCL run"
     dist.barrier()
     if rank == 0 and ok:
         print("LP_WORKER_OK")

@@ -148,7 +148,7 @@ def _full_window0(c):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (run under gpurun --gpus 2)")
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [w for w in (2, 4, 8) if w <= max(torch.cuda.device_count(), 2)])
 def test_engine_lp_over_nccl_matches_single_gpu(world):
     """Real NCCL run: torchrun x `world` ranks, lade.config_lade(DIST_WORKERS=world); ids == single-GPU ids."""
     import subprocess
@@ -159,3 +159,4 @@ def test_engine_lp_over_nccl_matches_single_gpu(world):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "LP_WORKER_OK" in res.stdout
+    print(res.stdout[-1500:])
