@@ -286,6 +286,7 @@ class LookaheadEngine:
         commit=False stops after the row-wise argmax (the sampling path decides on the host)."""
         lib, L = self.lib, self.L
         n = 0
+        skip = getattr(self, "_ablate", ())      # tools/step_ablation.py: leave kernels out to time the rest (results garbage)
         # prefill (step 0) is plain causal and carries no rowmask; every later step has one and must fit it
         mw = 0 if prefill else self.mask_words
         if mw and rows > (mw - 1) * 32:
@@ -303,26 +304,35 @@ class LookaheadEngine:
         pf = self.prefetch_mb if (self.l2_prefetch and not prefill) else (0, 0, 0, 0, 0)
         for l in range(L):
             n += self._prefetch([(self.w_qkv[l], 0)], pf[0])                              # beside rmsnorm
-            check(lib.lade_rmsnorm(stream, _ptr(h), _ptr(delta), _ptr(self.ln1[l]), _ptr(h) if delta is not None else 0,
-                                   _ptr(xn), rows, self.H, self.eps), "lade_rmsnorm"); n += 1
-            torch.mm(xn, self.w_qkv[l].t(), out=qkv)
+            if "norm" not in skip:
+                check(lib.lade_rmsnorm(stream, _ptr(h), _ptr(delta), _ptr(self.ln1[l]), _ptr(h) if delta is not None else 0,
+                                       _ptr(xn), rows, self.H, self.eps), "lade_rmsnorm"); n += 1
+            if "gemm" not in skip:
+                torch.mm(xn, self.w_qkv[l].t(), out=qkv)
             n += self._prefetch([(self.w_o[l], 0), (self.w_gu[l], 0)], pf[1])              # beside rope + attention
             kc, vc = self.kv[l, 0], self.kv[l, 1]
-            check(lib.lade_rope_append(stream, _ptr(qkv), _ptr(self.cos), _ptr(self.sin), _ptr(self.pos), _ptr(self.meta),
-                                       _ptr(qb), _ptr(kc), _ptr(vc), rows, rows, self.nh, self.nkv, self.D,
-                                       self.kv_capacity, self.table_len), "lade_rope_append"); n += 1
-            check(lib.lade_attn_fwd(stream, _ptr(qb), _ptr(kc), _ptr(vc), _ptr(attn_out), _ptr(self.rowmask) if mw else 0, mw,
-                                    _ptr(self.meta), _ptr(self.attn_scratch), rows, self.nh, self.nkv, self.D,
-                                    self.kv_capacity, kv_bound, self.attn_splits, self.attn_impl), "lade_attn_fwd"); n += 1
-            torch.mm(attn_out, self.w_o[l].t(), out=o_buf)
+            if "rope" not in skip:
+                check(lib.lade_rope_append(stream, _ptr(qkv), _ptr(self.cos), _ptr(self.sin), _ptr(self.pos), _ptr(self.meta),
+                                           _ptr(qb), _ptr(kc), _ptr(vc), rows, rows, self.nh, self.nkv, self.D,
+                                           self.kv_capacity, self.table_len), "lade_rope_append"); n += 1
+            if "attn" not in skip:
+                check(lib.lade_attn_fwd(stream, _ptr(qb), _ptr(kc), _ptr(vc), _ptr(attn_out), _ptr(self.rowmask) if mw else 0, mw,
+                                        _ptr(self.meta), _ptr(self.attn_scratch), rows, self.nh, self.nkv, self.D,
+                                        self.kv_capacity, kv_bound, self.attn_splits, self.attn_impl), "lade_attn_fwd"); n += 1
+            if "gemm" not in skip:
+                torch.mm(attn_out, self.w_o[l].t(), out=o_buf)
             gu_done = max(0, int(pf[1] * 1e6) - self.w_o[l].numel() * 2) & ~15
             n += self._prefetch([(self.w_gu[l], gu_done)], pf[2])                          # beside rmsnorm
-            check(lib.lade_rmsnorm(stream, _ptr(h), _ptr(o_buf), _ptr(self.ln2[l]), _ptr(h), _ptr(xn), rows, self.H,
-                                   self.eps), "lade_rmsnorm"); n += 1
-            torch.mm(xn, self.w_gu[l].t(), out=gu)
+            if "norm" not in skip:
+                check(lib.lade_rmsnorm(stream, _ptr(h), _ptr(o_buf), _ptr(self.ln2[l]), _ptr(h), _ptr(xn), rows, self.H,
+                                       self.eps), "lade_rmsnorm"); n += 1
+            if "gemm" not in skip:
+                torch.mm(xn, self.w_gu[l].t(), out=gu)
             n += self._prefetch([(self.w_down[l], 0)], pf[3])                              # beside swiglu
-            check(lib.lade_swiglu(stream, _ptr(gu), _ptr(act), rows, self.I), "lade_swiglu"); n += 1
-            torch.mm(act, self.w_down[l].t(), out=d_buf)
+            if "swiglu" not in skip:
+                check(lib.lade_swiglu(stream, _ptr(gu), _ptr(act), rows, self.I), "lade_swiglu"); n += 1
+            if "gemm" not in skip:
+                torch.mm(act, self.w_down[l].t(), out=d_buf)
             delta = d_buf
         n += self._prefetch([(self.lm_head, 0)], pf[4])                                    # beside the final norm
         check(lib.lade_rmsnorm_gather(stream, _ptr(h), _ptr(delta), _ptr(self.norm_w), _ptr(self.lm_rows),

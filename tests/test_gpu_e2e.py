@@ -160,3 +160,38 @@ def test_unsupported_inputs_fail_loudly():
     with pytest.raises(LadeError):
         jacobi_greedy_search_multilevel(model, torch.ones(1, 4, dtype=torch.long, device="cuda"),
                                         return_dict_in_generate=True)
+
+
+def test_eval_harness_loop_totals_are_consistent(monkeypatch):
+    """The eval_mtbench.py-shaped timing loop over synthetic multi-turn prompts (lookaheaddecoding_b200/eval_harness.py):
+    per-turn stats add up, conversations grow turn by turn, and lade.log_history() sees every generate()."""
+    import contextlib
+    import io
+    import lade
+    from lookaheaddecoding_b200.decoding import CONFIG_MAP
+    from lookaheaddecoding_b200.eval_harness import run_eval, synthetic_questions
+    c = CASES["tiny_bf16_w5n3g3"]
+    model, _ = build_hf_llama(c["model"], c["weight_seed"])
+    model.generation_config.pad_token_id = 0
+    model.generation_config.eos_token_id = None
+    monkeypatch.setenv("USE_LADE", "1")
+    lade.augment_all()
+    try:
+        lade.config_lade(LEVEL=4, WINDOW_SIZE=7, GUESS_SET_SIZE=7, DEBUG=1, POOL_FROM_PROMPT=True)
+        qs = synthetic_questions(3, 2, 20, c["model"]["vocab"], seed=3)
+        with contextlib.redirect_stdout(io.StringIO()):
+            rep = run_eval(model, qs, max_new_token=24, temperature=0.0)
+            rep_s = run_eval(model, qs[:1], max_new_token=16, temperature=0.7)
+        assert rep.count_gen == 6 and rep.overall_gen == 6 * 24
+        assert sum(v[1] for q in rep.stats.values() for v in q.values()) == rep.overall_gen
+        assert abs(sum(v[0] for q in rep.stats.values() for v in q.values()) - rep.overall_time) < 1e-6
+        assert rep.throughput_overall > 0 and "AVERAGE THROUGHPUT1" in rep.summary()
+        assert rep_s.count_gen == 2 and rep_s.overall_gen == 32
+        log = CONFIG_MAP["log"]
+        assert len(log) == 8 and sum(e[0] for e in log[:6]) == rep.overall_gen
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            lade.log_history()
+        assert "OVERALL GEN:  176" in buf.getvalue()
+    finally:
+        lade.restore_generate()
