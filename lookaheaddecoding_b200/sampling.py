@@ -23,6 +23,7 @@ import ctypes as C
 import random
 from typing import List, Optional
 
+import numpy as np
 import torch
 
 from . import _cabi
@@ -105,40 +106,34 @@ def sample_lookahead(eng, prompt: List[int], max_new_tokens: int, logits_warper,
             probs = torch.nn.functional.softmax(next_token_scores, dim=-1)
             next_tokens = torch.multinomial(probs, num_samples=1).squeeze(1)
             hits = [next_tokens.item()]
-        else:                                                                              # :484-540
-            guess_tokens = eng.ids[meta[_cabi.M_Q_LEN] - lg: meta[_cabi.M_Q_LEN]].cpu().tolist()
-            probs_next = torch.nn.functional.softmax(next_token_scores, dim=-1)[0]
+        else:
+            # Candidate verification with the HOST random streams (fixed-seed compatibility with the reference's
+            # draws, decoding.py:484-540): a uniform from python's `random` per accept test, torch.multinomial for the
+            # residual draw.  Probabilities stay on the device; only the probability of the token under test and the
+            # drawn token cross to the host.
+            q_len = meta[_cabi.M_Q_LEN]
+            grams = np.asarray(eng.ids[q_len - lg:q_len].cpu().tolist(), dtype=np.int64).reshape(-1, GS)
+            slot_probs = torch.nn.functional.softmax(warp(input_ids, eng.logits[1 + WCAP:1 + WCAP + lg].float()), dim=-1)
+            dist = torch.nn.functional.softmax(next_token_scores, dim=-1)[0]      # distribution of the token being decided
+            alive = np.ones(len(grams), dtype=bool)
             hits = []
-            guess_logits = warp(input_ids, eng.logits[1 + WCAP:1 + WCAP + lg].float())
-            guess_probs = torch.nn.functional.softmax(guess_logits, dim=-1)
-            guess_indices = list(range(lg // GS))
-            for idx_in_ngram in range(GS):
-                g_idx = 0
-                is_accept = False
-                while g_idx < len(guess_indices):
-                    guess_idx = guess_indices[g_idx]
-                    guess_offset = guess_idx * GS
-                    draft_guess = guess_tokens[guess_offset + idx_in_ngram]
-                    prob_accept = min(1, probs_next[draft_guess].item())
-                    sample_prob = rnd.random()
-                    if sample_prob < prob_accept:
-                        hits.append(draft_guess)
-                        is_accept = True
-                        max_hit_idx = guess_idx
-                        guess_indices = [gi for gi in guess_indices
-                                         if guess_tokens[gi * GS + idx_in_ngram] == draft_guess]
+            for pos in range(GS):
+                winner = -1
+                for cand in np.flatnonzero(alive):
+                    tok = int(grams[cand, pos])
+                    if rnd.random() < min(1, dist[tok].item()):                 # :505-508
+                        winner = int(cand)
                         break
-                    else:
-                        probs_next[draft_guess] = 0
-                        probs_next = probs_next / probs_next.sum()
-                        g_idx += 1
-                if is_accept:
-                    probs_next = guess_probs[guess_offset + idx_in_ngram]
-                    continue
-                else:
-                    new_token_gen = torch.multinomial(probs_next, num_samples=1).item()
-                    hits.append(new_token_gen)
+                    dist[tok] = 0                                               # :518-520
+                    dist = dist / dist.sum()
+                if winner < 0:
+                    hits.append(torch.multinomial(dist, num_samples=1).item())  # :533-535
                     break
+                tok = int(grams[winner, pos])
+                hits.append(tok)
+                max_hit_idx = winner
+                alive &= grams[:, pos] == tok                                   # :513-516
+                dist = slot_probs[winner * GS + pos]                            # :530
             max_hit = len(hits) - 1
         if phase == 2 and eos:                                                             # :578-580
             filtered = list(new_results)          # the pool was already fed the unfiltered row (:563)
