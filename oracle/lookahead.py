@@ -7,11 +7,11 @@ hao-ai-lab/LookaheadDecoding (citations are ``/root/reference/...`` file:line). 
 (``lookaheaddecoding_b200``) never does.
 
 Parity status: PINNED.  The reference ships no tests or golden vectors, so this
-restatement is pinned against the reference *itself*, executed unmodified from /root/reference
-through ``oracle/ref_shim.py``: per-step traces (step rows, position ids, masks, argmax tokens,
-hits, pool contents, final ids) are committed under ``tests/golden/`` by
-``tests/golden/gen_golden.py`` and checked by ``tests/test_oracle_golden.py``; when
-/root/reference is present the same comparison also runs live (``tests/test_oracle_vs_reference.py``).
+restatement is pinned against the reference *itself*, executed unmodified through
+``baseline/ref_loader.py`` (``oracle/ref_shim.py`` is its old import path): per-step traces (step rows,
+position ids, masks, argmax tokens, hits, pool contents, final ids) are committed under ``tests/golden/`` by
+``tests/golden/gen_golden*.py`` and checked by ``tests/test_oracle_golden.py``, ``test_oracle_edge.py``,
+``test_oracle_pool.py``, ``test_oracle_sampling.py`` and ``test_lp_gloo.py``.
 
 Vocabulary follows the reference: LEVEL (N), WINDOW_SIZE (W), GUESS_SET_SIZE (G), guess size = N-1,
 ``past_tokens`` = the 2-D lookahead window (N-1 levels), ``token_map`` = the n-gram pool,
