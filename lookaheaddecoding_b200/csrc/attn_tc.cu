@@ -32,6 +32,10 @@ constexpr int TC_XCH_FLOATS = 512;   // 2 KB: row maxima (bf16 [2][4][128]) / ro
 constexpr int TC_SMEM_TILES = TC_TILE_BYTES * (1 + 2 * TC_STAGES);
 constexpr int TC_SMEM_BYTES = TC_SMEM_TILES + 256 + TC_XCH_FLOATS * 4;
 constexpr float TC_LOG2E = 1.4426950408889634f;
+// DSMEM merge transport (merge_mode 1): slots in the owner's dead K/V stages, (m, l) in its dead Q tile
+constexpr int TC_SO_STRIDE = 132;                       // floats per staged O row (528 B: conflict-free float4 rows)
+constexpr int TC_SO_OFFSET = TC_TILE_BYTES;
+constexpr int TC_SML_OFFSET = 0;
 
 __host__ __device__ constexpr uint32_t umma_idesc(bool b_mn_major) { return umma_idesc_n(128u, b_mn_major); }
 
@@ -50,7 +54,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out,
                    const uint32_t* __restrict__ rowmask, int mask_words, const int* __restrict__ meta, int q_pad,
                    int n_heads, int n_kv_heads, int n_splits, float inv_sqrt_d, float* __restrict__ part_o,
-                   float2* __restrict__ part_ml) {
+                   float2* __restrict__ part_ml, int merge_mode) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int split = blockIdx.x, h = blockIdx.y, mt = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -383,6 +387,71 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int per = (TC_BM + n_active - 1) / n_active;
   int dest = -1;
   const long long hm = (long long)h * gridDim.z + mt;
+  if (merge_mode == 1) {
+    // ---- alternative transport (LADE_ATTN_MERGE=dsmem): push through distributed shared memory -----------------
+    // slot k of an owner CTA = [per][TC_SO_STRIDE] floats in its (dead) K/V stages; barrier 1 = every CTA is done with
+    // its stages, barrier 2 = the pushes have landed.  Same arithmetic as below; measured no faster than the L2 path
+    // (the SM-to-SM network moves ~17 B/clk per SM in either direction).
+    cluster_arrive();
+    cluster_wait();
+    TC_STAMP(TS_CLUSTER, 0);
+    int r_in = 0;
+    if (active && warp >= 2) {
+      const int row_l = (warp & 3) * 32 + lane;
+      const int q4 = (warp - 2) >> 2;
+      dest = row_l / per;
+      r_in = row_l - dest * per;
+      if (dest != split) {
+        const int slot = split < dest ? split : split - 1;
+        const uint32_t o_a = dsmem_addr(sQ_a + TC_SO_OFFSET + (uint32_t)(((slot * per + r_in) * TC_SO_STRIDE + q4 * 32) * 4), dest);
+#pragma unroll
+        for (int v4 = 0; v4 < 8; ++v4) st_dsmem_f4(o_a + v4 * 16, ov[v4 * 4], ov[v4 * 4 + 1], ov[v4 * 4 + 2], ov[v4 * 4 + 3]);
+        if (q4 == 0) st_dsmem_f2(dsmem_addr(sQ_a + TC_SML_OFFSET + (uint32_t)((slot * per + r_in) * 8), dest), m_row, l_row);
+      }
+    }
+    cluster_arrive();
+    cluster_wait();
+    TC_STAMP(TS_MERGED, 0);
+    if (active && warp >= 2 && dest == split) {
+      const int row_l = (warp & 3) * 32 + lane;
+      const int q4 = (warp - 2) >> 2;
+      const int row = mt * TC_BM + row_l;
+      const float2* sml = reinterpret_cast<const float2*>(smem + TC_SML_OFFSET);
+      const float* so = reinterpret_cast<const float*>(smem + TC_SO_OFFSET);
+      float mmax = m_row;
+      for (int k = 0; k < n_active - 1; ++k) mmax = fmaxf(mmax, sml[k * per + r_in].x);
+      float wgt = (m_row == -INFINITY) ? 0.f : exp2f((m_row - mmax) * TC_LOG2E);
+      float lsum = l_row * wgt;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) ov[i] *= wgt;
+      for (int k = 0; k < n_active - 1; ++k) {
+        const float2 ml = sml[k * per + r_in];
+        wgt = (ml.x == -INFINITY) ? 0.f : exp2f((ml.x - mmax) * TC_LOG2E);
+        lsum += ml.y * wgt;
+        const float4* src = reinterpret_cast<const float4*>(so + (k * per + r_in) * TC_SO_STRIDE + q4 * 32);
+#pragma unroll
+        for (int v4 = 0; v4 < 8; ++v4) {
+          const float4 x = src[v4];
+          ov[v4 * 4] += x.x * wgt; ov[v4 * 4 + 1] += x.y * wgt; ov[v4 * 4 + 2] += x.z * wgt; ov[v4 * 4 + 3] += x.w * wgt;
+        }
+      }
+      const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
+      if (row < q_pad) {
+        uint4* dst = reinterpret_cast<uint4*>(out + (long long)row * HD + h * TC_D + q4 * 32);
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4) {
+          uint4 pk;
+          pk.x = pack2_bf16(ov[v4 * 8 + 0] * inv, ov[v4 * 8 + 1] * inv);
+          pk.y = pack2_bf16(ov[v4 * 8 + 2] * inv, ov[v4 * 8 + 3] * inv);
+          pk.z = pack2_bf16(ov[v4 * 8 + 4] * inv, ov[v4 * 8 + 5] * inv);
+          pk.w = pack2_bf16(ov[v4 * 8 + 6] * inv, ov[v4 * 8 + 7] * inv);
+          dst[v4] = pk;
+        }
+      }
+    }
+    TC_STAMP(TS_END, 0);
+    return;
+  }
   if (active && warp >= 2) {
     const int row_l = (warp & 3) * 32 + lane;
     const int q4 = (warp - 2) >> 2;
@@ -503,6 +572,15 @@ static int get_tensor_map(const void* ptr, int rows, int heads, CUtensorMap* out
   return LADE_OK;
 }
 
+static int merge_mode() {          // LADE_ATTN_MERGE=dsmem selects the DSMEM push transport (default: L2 scratch)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LADE_ATTN_MERGE");
+    v = (e && e[0] == 'd') ? 1 : 0;
+  }
+  return v;
+}
+
 static bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -555,7 +633,7 @@ int attn_fwd_tc_launch(cudaStream_t stream, const void* q, const void* k_cache, 
   float* part_o = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 65536);
   float2* part_ml = reinterpret_cast<float2*>(part_o + (size_t)n_splits * n_heads * q_tiles * TC_BM * TC_D);
   cudaError_t e = cudaLaunchKernelEx(&cfg, attn_fwd_tc_kernel, tmQ, tmK, tmV, (__nv_bfloat16*)out, rowmask, mask_words, meta,
-                                     q_pad, n_heads, n_kv_heads, n_splits, inv_sqrt_d, part_o, part_ml);
+                                     q_pad, n_heads, n_kv_heads, n_splits, inv_sqrt_d, part_o, part_ml, merge_mode());
   if (e != cudaSuccess) { set_cuda_error(e, "cudaLaunchKernelEx(attn_fwd_tc_kernel)"); return LADE_ECUDA; }
   return LADE_OK;
 }

@@ -15,14 +15,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // One CTA per row.  h = bf16(x + delta) (if delta), out = w * bf16(h_f32 * rsqrt(mean(h^2) + eps)).
 template <bool GATHER>
-__global__ void __launch_bounds__(256) rmsnorm_kernel(const __nv_bfloat16* __restrict__ x,
+__global__ void __launch_bounds__(1024) rmsnorm_kernel(const __nv_bfloat16* __restrict__ x,
                                                       const __nv_bfloat16* __restrict__ delta,
                                                       const __nv_bfloat16* __restrict__ w,
                                                       const int* __restrict__ rows_idx,
                                                       __nv_bfloat16* __restrict__ h_out,
                                                       __nv_bfloat16* __restrict__ out, int hidden, float eps) {
   extern __shared__ float s_row[];  // hidden floats
-  __shared__ float s_part[8];
+  __shared__ float s_part[32];
   const int out_row = blockIdx.x;
   const int in_row = GATHER ? rows_idx[out_row] : out_row;
   const __nv_bfloat16* xr = x + (long long)in_row * hidden;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const __nv_bfloat16* __res
 // RoPE + append.  grid: rows ; block: 256 threads.  Work item = (head, 8-wide slice of the first half):
 // the thread rotates elements [8i, 8i+8) of the first half against the same slice of the second half,
 // all accesses 16 bytes.  (Hq + 2 Hkv) * D/16 items per row.
-__global__ void __launch_bounds__(256) rope_append_kernel(
+__global__ void __launch_bounds__(1024) rope_append_kernel(
     const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ cos_tab,
     const __nv_bfloat16* __restrict__ sin_tab, const int* __restrict__ pos, const int* __restrict__ meta,
     __nv_bfloat16* __restrict__ q_out, __nv_bfloat16* __restrict__ k_cache, __nv_bfloat16* __restrict__ v_cache,
@@ -184,6 +184,11 @@ using namespace lade;
 
 extern "C" {
 
+static int norm_threads(int hidden) {
+  int t = ((hidden / 8 + 31) / 32) * 32;
+  return t < 128 ? 128 : (t > 1024 ? 1024 : t);
+}
+
 int lade_l2_prefetch(void* stream, const void* ptr, int64_t bytes, int32_t n_ctas, int32_t chunk_bytes) {
   if (!ptr || bytes < 0 || n_ctas < 1 || chunk_bytes < 16 || (chunk_bytes & 15) || (reinterpret_cast<uintptr_t>(ptr) & 15))
     return LADE_EINVAL;
@@ -201,7 +206,9 @@ int lade_rmsnorm(void* stream, const void* x, const void* delta, const void* wei
   if (smem > 96 * 1024) return LADE_EUNSUPPORTED;
   if (smem > 48 * 1024)
     LADE_CUDA_CHECK(cudaFuncSetAttribute(rmsnorm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  rmsnorm_kernel<false><<<rows, 256, smem, (cudaStream_t)stream>>>(
+  // one 16-byte vector per thread when the row fits (4096 / 8 = 512 threads): a single round of loads per phase
+  const int threads = norm_threads(hidden);
+  rmsnorm_kernel<false><<<rows, threads, smem, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x, (const __nv_bfloat16*)delta, (const __nv_bfloat16*)weight, nullptr,
       (__nv_bfloat16*)h_out, (__nv_bfloat16*)out, hidden, eps);
   LADE_LAUNCH_CHECK("rmsnorm_kernel");
@@ -215,7 +222,8 @@ int lade_rmsnorm_gather(void* stream, const void* x, const void* delta, const vo
   if (smem > 96 * 1024) return LADE_EUNSUPPORTED;
   if (smem > 48 * 1024)
     LADE_CUDA_CHECK(cudaFuncSetAttribute(rmsnorm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  rmsnorm_kernel<true><<<n_rows, 256, smem, (cudaStream_t)stream>>>(
+  const int threads = norm_threads(hidden);
+  rmsnorm_kernel<true><<<n_rows, threads, smem, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x, (const __nv_bfloat16*)delta, (const __nv_bfloat16*)weight, rows_idx, nullptr,
       (__nv_bfloat16*)out, hidden, eps);
   LADE_LAUNCH_CHECK("rmsnorm_gather_kernel");
@@ -228,7 +236,10 @@ int lade_rope_append(void* stream, const void* qkv, const void* cos_tab, const v
                      int32_t kv_capacity, int32_t max_pos) {
   if (!qkv || !cos_tab || !sin_tab || !pos || !meta || !q_out || !k_cache || !v_cache) return LADE_EINVAL;
   if (rows < 1 || rows > q_pad || head_dim % 16 != 0 || head_dim > 512 || n_heads < 1 || n_kv_heads < 1) return LADE_EINVAL;
-  rope_append_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(
+  // one work item (head, 8-wide slice) per thread when they fit: (32 + 2*32) heads * 8 slices = 768 threads at 7B
+  int rope_threads = (((n_heads + 2 * n_kv_heads) * (head_dim / 16) + 31) / 32) * 32;
+  rope_threads = rope_threads < 128 ? 128 : (rope_threads > 1024 ? 1024 : rope_threads);
+  rope_append_kernel<<<rows, rope_threads, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)cos_tab, (const __nv_bfloat16*)sin_tab, pos, meta,
       (__nv_bfloat16*)q_out, (__nv_bfloat16*)k_cache, (__nv_bfloat16*)v_cache, q_pad, n_heads, n_kv_heads,
       head_dim, kv_capacity, max_pos);

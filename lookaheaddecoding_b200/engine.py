@@ -480,6 +480,7 @@ class LookaheadEngine:
         self._graph_n = n
         return g
 
+    @torch.no_grad()
     def run_forward_step(self, step: int, n_prompt: int, commit: bool = True) -> None:
         """One step's launches (eager for the prefill / window-fill steps, graph replay afterwards)."""
         stream = torch.cuda.current_stream(self.dev).cuda_stream

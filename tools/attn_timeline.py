@@ -32,10 +32,19 @@ for kv, ns in [(1024, 4), (3072, 4)]:
     run(0)
     torch.cuda.synchronize()
     _cabi.check(lib.lade_debug_attn_timing(0))
-    t = tb.cpu().numpy().reshape(-1, 16).astype(np.float64)
-    t = t[t[:, 0] > 0]
+    t_all = tb.cpu().numpy().reshape(-1, 16).astype(np.float64)          # CTA order: head-major, split fastest
+    per_split = {}
+    for sp in range(ns):
+        ts = t_all[sp::ns]
+        ts = ts[ts[:, 0] > 0]
+        if len(ts):
+            per_split[sp] = {"ofinal": round(float(np.median((ts[:, 3] - ts[:, 0]) / 1.965e3)), 2),
+                             "compute_done": round(float(np.median((ts[:, 4] - ts[:, 0]) / 1.965e3)), 2),
+                             "start_skew": round(float(np.median((ts[:, 0] - t_all[0::ns][:len(ts), 0]) / 1.965e3)), 2)}
+    t = t_all[t_all[:, 0] > 0]
     names = ["start", "kfull0", "sfull0", "ofinal", "compute_done", "barrier1", "pushed_barrier2", "end", "t1_begin", "t1_sfull", "t1_ld", "t1_max", "t1_bar", "t1_exp", "t1_fence", "t1_arrive"]
     rel = (t - t[:, :1]) / 1.965e3     # us at 1965 MHz
     print(json.dumps({"kv": kv, "splits": ns, "ctas": int(len(t)),
-                      "median_us_since_start": {n: round(float(np.median(rel[:, i])), 2) for i, n in enumerate(names)},
-                      }))
+                      "median_us_since_start": {n: round(float(np.median(rel[:, i])), 2) for i, n in enumerate(names)
+                                                if np.median(t[:, i]) > 0},
+                      "per_split_us": per_split}))
