@@ -375,23 +375,22 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   TC_STAMP(TS_STAGED, 0);
   if (n_splits == 1) { TC_STAMP(TS_END, 0); return; }
 
-  // ---- split merge across the cluster, through global memory (L2) ----
+  // ---- split merge across the cluster ----
   // Row r of the tile is owned by CTA r / per (per = ceil(128 / n_active)).  Every softmax thread holds 32 fp32 of
-  // its split's unnormalised O row (and the row's (m, l)) in registers: threads whose row belongs to a sibling store
-  // them to the split's slab of the scratch buffer (plain coalescable 16-byte stores: L2 takes ~64 B/clk per SM,
-  // the SM-to-SM network measured ~17 B/clk both for remote loads and for remote stores -- 3.3 us for the 48 KB a
-  // CTA exchanges), threads of owned rows keep theirs.  One cluster barrier (release / acquire) publishes the slabs;
-  // the owner threads then combine their registers with the n_active-1 sibling slabs read back from L2:
-  //   w_s = 2^(m_s - m),  out = sum_s w_s O_s / sum_s w_s l_s.
-  // The slabs live in a 6 MB scratch that is rewritten by every launch and never leaves the L2.
+  // its split's unnormalised O row (and the row's (m, l)) in registers; threads of owned rows keep theirs, the others
+  // ship theirs to the owner, who combines:  w_s = 2^(m_s - m),  out = sum_s w_s O_s / sum_s w_s l_s.
+  // Transport 0 (LADE_ATTN_MERGE=l2, kept for A/B): the split's slab of an L2-resident scratch + one cluster barrier.
   const int per = (TC_BM + n_active - 1) / n_active;
   int dest = -1;
   const long long hm = (long long)h * gridDim.z + mt;
   if (merge_mode == 1) {
-    // ---- alternative transport (LADE_ATTN_MERGE=dsmem): push through distributed shared memory -----------------
-    // slot k of an owner CTA = [per][TC_SO_STRIDE] floats in its (dead) K/V stages; barrier 1 = every CTA is done with
-    // its stages, barrier 2 = the pushes have landed.  Same arithmetic as below; measured no faster than the L2 path
-    // (the SM-to-SM network moves ~17 B/clk per SM in either direction).
+    // ---- default transport: PUSH through distributed shared memory ------------------------------------------------
+    // Threads of foreign rows store their 32 registers straight into the owner CTA's shared memory (st.shared::cluster,
+    // fire and forget: no local staging, no dependent remote loads).  Slot k of an owner = [per][TC_SO_STRIDE] floats in
+    // its (dead) K/V stages; barrier 1 = every CTA is done with its stages, barrier 2 = the pushes have landed; the
+    // owner threads then combine their own registers with the slots from LOCAL shared memory.  Same-box A/B
+    // (profiles/r02_attn_merge_ab.jsonl): 15.2 us per launch at the bench shape against 18.6 us for the L2 transport
+    // below and 16.9 us for round 1's pull (stage locally, siblings read over DSMEM).
     cluster_arrive();
     cluster_wait();
     TC_STAMP(TS_CLUSTER, 0);
@@ -572,11 +571,11 @@ static int get_tensor_map(const void* ptr, int rows, int heads, CUtensorMap* out
   return LADE_OK;
 }
 
-static int merge_mode() {          // LADE_ATTN_MERGE=dsmem selects the DSMEM push transport (default: L2 scratch)
+static int merge_mode() {          // default: DSMEM push (1); LADE_ATTN_MERGE=l2 selects the L2-scratch transport (0)
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("LADE_ATTN_MERGE");
-    v = (e && e[0] == 'd') ? 1 : 0;
+    v = (e && e[0] == 'l') ? 0 : 1;
   }
   return v;
 }
