@@ -669,6 +669,18 @@ def main():
             n_same = next((i for i in range(min(len(single), len(out))) if single[i] != out[i]), min(len(single), len(out)))
             lp_ids_equal = {"ranks_agree": ranks_agree, "equal_to_single_gpu": single == out,
                             "equal_prefix_tokens": n_same - P, "compared_tokens": len(out) - P}
+            if single != out and n_same < min(len(single), len(out)):
+                # a rank forwards 1/N of the window rows, so its GEMMs run at another M and round differently: judge the
+                # first divergence on the model's own logits (stock HF forward of the common prefix, same weights)
+                with torch.no_grad():
+                    lg = model(torch.tensor([out[:n_same]], device=dev)).logits[0, -1].float()
+                import math
+                top = lg.max().item()
+                ulp = 2.0 ** (math.floor(math.log2(abs(top))) - 7)
+                lp_ids_equal["first_divergence"] = {
+                    "index": n_same - P, "lp_token_below_top_ulps": round((top - lg[out[n_same]].item()) / ulp, 2),
+                    "single_gpu_token_below_top_ulps": round((top - lg[single[n_same]].item()) / ulp, 2),
+                    "how": "both candidates judged on the stock HF forward of the common prefix (bf16 ulps of the top logit)"}
         dist.barrier()
     if rank != 0:
         if world > 1:
