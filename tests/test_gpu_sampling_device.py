@@ -179,10 +179,11 @@ def test_eos_stops_sampling_and_window_is_filtered():
     eos = full[32 + 20]
     first = next(i for i in range(32, len(full)) if full[i] == eos)
     cut = eng.generate(prompt, 64, eos_token_ids=[eos], rng=random.Random(1), sampling={"temperature": 0.02, "seed": 7})
-    # the run with EOS set follows the same draws until it stops (seeded Philox stream, same window), unless an EOS
-    # token in the newest window row was replaced by the filter -- then only the stop itself is checked
-    assert cut[-1] == eos and len(cut) <= first + 1 + 0 or cut[:len(cut) - 1] == full[:len(cut) - 1]
-    assert cut.count(eos) - prompt.count(eos) == 1 and len(cut) < len(full)
+    # EOS ends the run at its first occurrence (the emission loop of the commit kernel truncates the hits there,
+    # decoding.py:594-603); at T -> 0 the trajectory up to that point is the one of the run without EOS
+    gen = cut[32:]
+    assert cut[-1] == eos and gen.count(eos) == 1 and len(cut) <= first + 1
+    _assert_equal_up_to_a_tie(model, cut, full[:len(cut)], "eos run vs free run")
     eng.close()
 
 

@@ -155,3 +155,74 @@ def test_config_lade_joins_lookahead_workers_over_gloo(tmp_path):
                           "--master-addr", "127.0.0.1", "--master-port", "29581", str(script)],
                          capture_output=True, text=True, timeout=300)
     assert res.returncode == 0 and "LP_JOIN_OK" in res.stdout, res.stderr[-1500:]
+
+
+def test_extra_stopping_criteria_are_found_and_evaluated_on_the_host():
+    """MaxLength / EOS criteria are handled on the device; anything else is called after every step (decoding.py:1215)."""
+    from transformers import MaxLengthCriteria, StoppingCriteria, StoppingCriteriaList
+    from lookaheaddecoding_b200.decoding import _extra_stopping_criteria, _host_stop_fn
+
+    class StopOnToken(StoppingCriteria):
+        def __call__(self, input_ids, scores, **kw):
+            return torch.tensor([bool((input_ids[0] == 7).any())])
+
+    crit = StoppingCriteriaList([MaxLengthCriteria(40), StopOnToken()])
+    extra = _extra_stopping_criteria(crit)
+    assert len(extra) == 1 and isinstance(extra[0], StopOnToken)
+    assert _extra_stopping_criteria(StoppingCriteriaList([MaxLengthCriteria(4)])) == []
+    assert _host_stop_fn([], torch.device("cpu"), torch.long) is None
+    stop = _host_stop_fn(extra, torch.device("cpu"), torch.long)
+    assert stop([1, 2, 3]) is False and stop([1, 7, 3]) is True
+
+
+def test_device_sampling_is_chosen_for_temperature_only_warpers():
+    from transformers.generation.logits_process import (LogitsProcessorList, TemperatureLogitsWarper, TopKLogitsWarper,
+                                                        TopPLogitsWarper)
+    from lookaheaddecoding_b200.sampling import device_temperature
+    assert device_temperature(None) == 1.0 and device_temperature(LogitsProcessorList()) == 1.0
+    assert abs(device_temperature(LogitsProcessorList([TemperatureLogitsWarper(0.8)])) - 0.8) < 1e-9
+    assert device_temperature(LogitsProcessorList([TemperatureLogitsWarper(0.8), TopKLogitsWarper(50)])) is None
+    assert device_temperature(LogitsProcessorList([TopPLogitsWarper(0.9)])) is None
+
+
+def test_eval_harness_bookkeeping_matches_the_reference_summary():
+    """applications/eval_mtbench.py:384-389: THROUGHPUT1 = mean of per-call tokens/s, THROUGHPUT2 = tokens / seconds."""
+    from lookaheaddecoding_b200.eval_harness import EvalReport, run_eval, synthetic_questions
+    qs = synthetic_questions(2, 3, 5, vocab=100, seed=1)
+    assert len(qs) == 2 and all(len(q) == 3 and all(len(t) == 5 for t in q) for q in qs)
+    assert qs == synthetic_questions(2, 3, 5, vocab=100, seed=1) and qs != synthetic_questions(2, 3, 5, vocab=100, seed=2)
+
+    class FakeModel(torch.nn.Module):          # echoes the prompt and appends max_new_tokens zeros
+        def __init__(self):
+            super().__init__()
+            self.p = torch.nn.Parameter(torch.zeros(1))
+            self.calls = []
+
+        def generate(self, ids, max_new_tokens=0, **kw):
+            self.calls.append((ids.shape[1], kw.get("do_sample"), kw.get("temperature")))
+            return torch.cat([ids, torch.zeros(1, max_new_tokens, dtype=ids.dtype)], dim=1)
+
+    m = FakeModel()
+    rep = run_eval(m, qs, max_new_token=4, temperature=0.0, sync=lambda: None)
+    assert rep.count_gen == 6 and rep.overall_gen == 24
+    assert [c[0] for c in m.calls] == [5, 14, 23, 5, 14, 23]          # the conversation grows by turn + answer
+    assert all(c[1] is False for c in m.calls)
+    assert abs(rep.throughput_overall - rep.overall_gen / rep.overall_time) < 1e-9
+    assert "AVERAGE THROUGHPUT1" in rep.summary() and "STAT" in rep.summary()
+    m.calls.clear()
+    run_eval(m, qs[:1], max_new_token=2, temperature=0.7, sync=lambda: None, max_context=12)
+    assert all(c[1] is True and abs(c[2] - 0.7) < 1e-9 for c in m.calls)
+    assert max(c[0] for c in m.calls) <= 10                            # context clipped to max_context - max_new_token
+    r = EvalReport()
+    assert r.throughput_overall == 0 and r.throughput_mean_of_calls == 0
+
+
+def test_nccl_entry_points_degrade_without_a_communicator():
+    import ctypes as C
+    from lookaheaddecoding_b200 import _cabi
+    lib = _cabi.load()
+    assert lib.lade_nccl_available() in (0, 1)
+    assert lib.lade_nccl_comm_destroy(None) == _cabi.LADE_EINVAL
+    assert lib.lade_lp_exchange(None, None, None, None, None) == _cabi.LADE_EINVAL
+    assert lib.lade_sample_verify(None, None, None, 0, 0, None, None, C.c_float(1.0), None, None, None) == _cabi.LADE_EINVAL
+    assert lib.lade_l2_prefetch(None, None, 0, 1, 16) == _cabi.LADE_EINVAL
