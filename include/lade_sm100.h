@@ -211,7 +211,8 @@ int lade_argmax_rows(void* stream, const void* logits, int32_t n_rows, int32_t v
 int lade_accept_update(LadeCtx* ctx, void* stream, const int32_t* argmax_slots, const int32_t* meta,
                        int32_t* result);
 
-/* Sampling verification ON DEVICE for the warper set {temperature} -- replaces the host loop of
+/* Sampling verification ON DEVICE for the reference's warper set {temperature, top-k, top-p} (decoding.py:375-377;
+ * top_k = 0 and top_p = 1 switch the filters off) -- replaces the host loop of
  * jacobi_sample_multilevel, lade/decoding.py:445-546 (softmax of out_logits / T :445,:485; per n-gram position the
  * accept test u < min(1, p[token]) over the n-grams still alive :495-516, zero-and-renormalise on reject :518-520,
  * residual multinomial draw :533-535; single multinomial draw on steps without candidates :458-480,:543-546) and
@@ -220,10 +221,13 @@ int lade_accept_update(LadeCtx* ctx, void* stream, const int32_t* argmax_slots, 
  * from a CUDA graph with no host round trip.  `logits`: bf16 [lm slots][ld], slot order of lade_step_layout's
  * lm_rows; `argmax_slots`: lade_argmax_rows of the same slots (the window advances by argmax, :466,:478,:549).
  * Writes the decision record lade_commit_decision consumes.  `debug_uniforms` (nullable, device float[>= 2 + G*(N-1) + W]):
- * [count, u0, u1, ...] the uniforms consumed, for tests.  Top-k / top-p warpers stay on the host-mirror path. */
+ * [count, u0, u1, ...] the uniforms consumed, for tests.  Top-k keeps every score >= the k-th largest (ties included,
+ * TopKLogitsWarper); top-p drops scores in ascending order while their cumulative probability stays <= 1 - top_p
+ * (TopPLogitsWarper, min_tokens_to_keep = 1) -- the logits are bf16, so both cut-offs are exact thresholds found with
+ * two 256-bin histogram passes, and scores of equal value are kept or dropped together. */
 int lade_sample_verify(LadeCtx* ctx, void* stream, const void* logits, int32_t ld, int32_t vocab,
-                       const int32_t* argmax_slots, const int32_t* meta, float temperature, uint64_t* rng_state,
-                       int32_t* decision_out, float* debug_uniforms);
+                       const int32_t* argmax_slots, const int32_t* meta, float temperature, int32_t top_k, float top_p,
+                       uint64_t* rng_state, int32_t* decision_out, float* debug_uniforms);
 
 /* Apply an externally made decision (sampling path: the caller runs the reference's rejection-sampling
  * verification, lade/decoding.py:484-540, against the device logits with its own RNG streams).

@@ -54,7 +54,7 @@ _SIGNATURES = {
     "lade_argmax_rows": (C.c_int, [c_p, c_p, c_i32, c_i32, c_i32, c_p]),
     "lade_accept_update": (C.c_int, [c_p, c_p, c_p, c_p, c_p]),
     "lade_commit_decision": (C.c_int, [c_p, c_p, c_p, c_p, c_p]),
-    "lade_sample_verify": (C.c_int, [c_p, c_p, c_p, c_i32, c_i32, c_p, c_p, C.c_float, c_p, c_p, c_p]),
+    "lade_sample_verify": (C.c_int, [c_p, c_p, c_p, c_i32, c_i32, c_p, c_p, C.c_float, c_i32, C.c_float, c_p, c_p, c_p]),
     "lade_kv_compact": (C.c_int, [c_p, c_p, c_p, c_p, C.c_int64, c_i32, c_i32, c_i32, c_i32, c_i32]),
     "lade_ctx_output_ids": (C.c_int, [c_p, c_p, c_p, c_i32]),
     "lade_ctx_pool_snapshot": (C.c_int, [c_p, c_p, c_p, c_p]),

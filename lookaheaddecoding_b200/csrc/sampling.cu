@@ -1,5 +1,6 @@
 // Sampling verification on the device: the multi-candidate rejection test of the sampling lookahead loop
-// (lade/decoding.py:445-546, "modified SpecInfer"), for the warper set {temperature}.
+// (lade/decoding.py:445-546, "modified SpecInfer"), for the reference's warper set {temperature, top-k, top-p}
+// (decoding.py:375-377).
 //
 // Reference, per step (host python + eager torch, one .item() sync per candidate, decoding.py:506):
 //   probs_next = softmax(out_logits / T)                                              :445,:485
@@ -58,21 +59,106 @@ __device__ __forceinline__ float score_of(const __nv_bfloat16* row, int t, float
   return __bfloat162float(row[t]) / temperature;
 }
 
-struct RowStats { float mx, sum; };
+// bf16 bit pattern -> 16-bit key that orders like the value (the logits are bf16: at most 65536 distinct scores, so
+// top-k / top-p cut-offs are exact thresholds on this key, found with two 256-bin histograms instead of a sort)
+__device__ __forceinline__ unsigned key_of(__nv_bfloat16 x) {
+  const unsigned b = __bfloat16_as_ushort(x);
+  return (b & 0x8000u) ? (~b & 0xffffu) : (b | 0x8000u);
+}
 
-__device__ RowStats row_stats(const __nv_bfloat16* row, int vocab, float temperature, float* s_red) {
+// The warped distribution of one logits row: p[t] = (key(t) >= thr) * exp(score_t - mx) / sum.
+struct RowDist { float mx, sum; unsigned thr; };
+
+__device__ __forceinline__ float e_of(const __nv_bfloat16* row, int t, float temperature, const RowDist& d) {
+  return key_of(row[t]) >= d.thr ? __expf(score_of(row, t, temperature) - d.mx) : 0.f;
+}
+
+// TemperatureLogitsWarper -> TopKLogitsWarper (keep every score >= the k-th largest, ties included) ->
+// TopPLogitsWarper (ascending cumulative probability of the top-k-filtered softmax: drop while cum <= 1 - top_p;
+// min_tokens_to_keep = 1).  Scores tie in whole buckets of equal bf16 value; a bucket is dropped only when all of it
+// can go (torch.sort breaks such ties arbitrarily, so there is no reference order to follow inside a bucket).
+__device__ RowDist row_dist(const __nv_bfloat16* row, int vocab, float temperature, int top_k, float top_p, float* s_red,
+                            int* s_cnt, float* s_mass, int* s_sel) {
+  RowDist d;
   float mx = -INFINITY;
-  for (int t = threadIdx.x; t < vocab; t += blockDim.x) mx = fmaxf(mx, score_of(row, t, temperature));
-  mx = block_reduce_max(mx, s_red);
+  unsigned kmax = 0;
+  for (int t = threadIdx.x; t < vocab; t += blockDim.x) {
+    mx = fmaxf(mx, score_of(row, t, temperature));
+    kmax = max(kmax, key_of(row[t]));
+  }
+  d.mx = block_reduce_max(mx, s_red);
+  const unsigned top_key = (unsigned)block_reduce_max((float)kmax, s_red);        // 16-bit keys are exact in fp32
+  d.thr = 0;
+  if (top_k > 0 && top_k < vocab) {
+    for (int pass = 0; pass < 2; ++pass) {                   // pass 0: high byte, pass 1: low byte inside that bucket
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) s_cnt[i] = 0;
+      __syncthreads();
+      const unsigned hb = pass ? (unsigned)s_sel[0] : 0u;
+      for (int t = threadIdx.x; t < vocab; t += blockDim.x) {
+        const unsigned k = key_of(row[t]);
+        if (pass == 0) atomicAdd(&s_cnt[k >> 8], 1);
+        else if ((k >> 8) == hb) atomicAdd(&s_cnt[k & 255u], 1);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int cum = pass ? s_sel[1] : 0;                       // elements in strictly higher buckets
+        int b = 255;
+        for (; b > 0; --b) {
+          if (cum + s_cnt[b] >= top_k) break;
+          cum += s_cnt[b];
+        }
+        if (pass == 0) { s_sel[0] = b; s_sel[1] = cum; }
+        else s_sel[2] = b;
+      }
+      __syncthreads();
+    }
+    d.thr = ((unsigned)s_sel[0] << 8) | (unsigned)s_sel[2];
+    __syncthreads();
+  }
   float sm = 0.f;
-  for (int t = threadIdx.x; t < vocab; t += blockDim.x) sm += __expf(score_of(row, t, temperature) - mx);
-  sm = block_reduce_sum(sm, s_red);
-  return RowStats{mx, sm};
+  for (int t = threadIdx.x; t < vocab; t += blockDim.x)
+    if (key_of(row[t]) >= d.thr) sm += __expf(score_of(row, t, temperature) - d.mx);
+  d.sum = block_reduce_sum(sm, s_red);
+  if (top_p < 1.f) {
+    const float lim = (1.f - top_p) * d.sum;
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) s_mass[i] = 0.f;
+      __syncthreads();
+      const unsigned hb = pass ? (unsigned)s_sel[0] : 0u;
+      for (int t = threadIdx.x; t < vocab; t += blockDim.x) {
+        const unsigned k = key_of(row[t]);
+        if (k < d.thr) continue;
+        const float e = __expf(score_of(row, t, temperature) - d.mx);
+        if (pass == 0) atomicAdd(&s_mass[k >> 8], e);
+        else if ((k >> 8) == hb) atomicAdd(&s_mass[k & 255u], e);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float cum = pass ? s_red[0] : 0.f;                   // mass of the buckets already dropped (s_red[0]: scratch)
+        int b = 0;
+        for (; b < 255; ++b) {
+          if (!(cum + s_mass[b] <= lim)) break;              // this bucket crosses 1 - top_p: it stays
+          cum += s_mass[b];
+        }
+        if (pass == 0) s_sel[0] = b;
+        else s_sel[2] = b;
+        s_red[0] = cum;
+      }
+      __syncthreads();
+    }
+    unsigned thr_p = ((unsigned)s_sel[0] << 8) | (unsigned)s_sel[2];
+    const float dropped = s_red[0];
+    __syncthreads();
+    if (thr_p > top_key) thr_p = top_key;                    // min_tokens_to_keep = 1
+    if (thr_p > d.thr) { d.thr = thr_p; d.sum -= dropped; }
+  }
+  if (d.thr > top_key) d.thr = top_key;
+  return d;
 }
 
 // One draw from the distribution e_t = exp(score_t - mx) over t not in zset[0..n_z), by inverse CDF:
 // the smallest t whose running mass reaches u * total.  Each thread owns one contiguous chunk of the vocabulary.
-__device__ int multinomial_excluding(const __nv_bfloat16* row, int vocab, float temperature, float mx, float u,
+__device__ int multinomial_excluding(const __nv_bfloat16* row, int vocab, float temperature, const RowDist& rd, float u,
                                      const int* zset, int n_z, float* s_scan, int* s_pick) {
   const int chunk = (vocab + blockDim.x - 1) / blockDim.x;
   const int lo = threadIdx.x * chunk, hi = min(vocab, lo + chunk);
@@ -80,7 +166,7 @@ __device__ int multinomial_excluding(const __nv_bfloat16* row, int vocab, float 
   for (int t = lo; t < hi; ++t) {
     bool z = false;
     for (int k = 0; k < n_z; ++k) z = z || (zset[k] == t);
-    if (!z) local += __expf(score_of(row, t, temperature) - mx);
+    if (!z) local += e_of(row, t, temperature, rd);
   }
   __syncthreads();
   s_scan[threadIdx.x] = local;
@@ -104,7 +190,7 @@ __device__ int multinomial_excluding(const __nv_bfloat16* row, int vocab, float 
       bool z = false;
       for (int k = 0; k < n_z; ++k) z = z || (zset[k] == t);
       if (z) continue;
-      const float e = __expf(score_of(row, t, temperature) - mx);
+      const float e = e_of(row, t, temperature, rd);
       if (e <= 0.f) continue;
       pick = t;                        // last live token of the chunk if rounding leaves `run` just short
       run += e;
@@ -119,7 +205,7 @@ __device__ int multinomial_excluding(const __nv_bfloat16* row, int vocab, float 
       for (int t = vocab - 1; t >= 0 && pick < 0; --t) {
         bool z = false;
         for (int k = 0; k < n_z; ++k) z = z || (zset[k] == t);
-        if (!z && __expf(score_of(row, t, temperature) - mx) > 0.f) pick = t;
+        if (!z && e_of(row, t, temperature, rd) > 0.f) pick = t;
       }
       *s_pick = pick < 0 ? 0 : pick;
     }
@@ -135,9 +221,12 @@ __device__ int multinomial_excluding(const __nv_bfloat16* row, int vocab, float 
 //    finished-by-extra-eos, 0, filtered[W]]
 __global__ void __launch_bounds__(SMP_THREADS, 1)
 sample_verify_kernel(int* st, Dims d, const __nv_bfloat16* __restrict__ logits, int ld, int vocab,
-                     const int* __restrict__ am, const int* __restrict__ meta, float temperature,
+                     const int* __restrict__ am, const int* __restrict__ meta, float temperature, int top_k, float top_p,
                      unsigned long long* rng_state, int* __restrict__ rec, float* dbg) {
   __shared__ float s_red[32];
+  __shared__ int s_cnt[256];
+  __shared__ float s_mass[256];
+  __shared__ int s_sel[4];
   __shared__ float s_scan[SMP_THREADS];
   __shared__ int s_pick;
   __shared__ int s_z[SMP_MAX_NGRAMS];           // tokens rejected at the current position
@@ -171,10 +260,10 @@ sample_verify_kernel(int* st, Dims d, const __nv_bfloat16* __restrict__ logits, 
 
   const __nv_bfloat16* row0 = logits;           // slot 0 = the next-token row (lade_step_layout's lm_rows)
   if (phase != 2 || n_ng == 0) {                // :458-480, :543-546
-    const RowStats rs = row_stats(row0, vocab, temperature, s_red);
+    const RowDist rs = row_dist(row0, vocab, temperature, top_k, top_p, s_red, s_cnt, s_mass, s_sel);
     if (t == 0) s_u = draw();
     __syncthreads();
-    const int tok = multinomial_excluding(row0, vocab, temperature, rs.mx, s_u, s_z, 0, s_scan, &s_pick);
+    const int tok = multinomial_excluding(row0, vocab, temperature, rs, s_u, s_z, 0, s_scan, &s_pick);
     if (t == 0) { s_hits[0] = tok; s_ctl[3] = 1; s_ctl[4] = 0; }
   } else {                                      // :484-540
     for (int e = t; e < n_ng; e += blockDim.x) s_alive[e] = 1;
@@ -183,7 +272,7 @@ sample_verify_kernel(int* st, Dims d, const __nv_bfloat16* __restrict__ logits, 
     for (int i = 0; i < GS; ++i) {
       const int cur = s_ctl[1];
       const __nv_bfloat16* row = logits + (long long)cur * ld;
-      const RowStats rs = row_stats(row, vocab, temperature, s_red);
+      const RowDist rs = row_dist(row, vocab, temperature, top_k, top_p, s_red, s_cnt, s_mass, s_sel);
       if (t == 0) {
         int n_z = 0;
         float zmass = 0.f;                      // probability mass rejected so far at this position
@@ -193,7 +282,7 @@ sample_verify_kernel(int* st, Dims d, const __nv_bfloat16* __restrict__ logits, 
           const int draft = gtok[e * GS + i];
           bool in_z = false;
           for (int k = 0; k < n_z; ++k) in_z = in_z || (s_z[k] == draft);
-          const float p_raw = __expf(score_of(row, draft, temperature) - rs.mx) / rs.sum;
+          const float p_raw = e_of(row, draft, temperature, rs) / rs.sum;
           const float denom = 1.f - zmass;
           const float p = in_z ? 0.f : (denom > 0.f ? p_raw / denom : 1.f);
           const float u = draw();
@@ -216,7 +305,7 @@ sample_verify_kernel(int* st, Dims d, const __nv_bfloat16* __restrict__ logits, 
       }
       __syncthreads();
       if (!s_ctl[0]) {                          // :533-535 residual draw, stop
-        const int tok = multinomial_excluding(row, vocab, temperature, rs.mx, s_u, s_z, s_ctl[2], s_scan, &s_pick);
+        const int tok = multinomial_excluding(row, vocab, temperature, rs, s_u, s_z, s_ctl[2], s_scan, &s_pick);
         if (t == 0) { s_hits[i] = tok; s_ctl[3] = i + 1; }
         __syncthreads();
         break;
@@ -274,14 +363,14 @@ using namespace lade;
 extern "C" {
 
 int lade_sample_verify(LadeCtx* ctx, void* stream, const void* logits, int32_t ld, int32_t vocab,
-                       const int32_t* argmax_slots, const int32_t* meta, float temperature, uint64_t* rng_state,
-                       int32_t* decision_out, float* debug_uniforms) {
+                       const int32_t* argmax_slots, const int32_t* meta, float temperature, int32_t top_k, float top_p,
+                       uint64_t* rng_state, int32_t* decision_out, float* debug_uniforms) {
   if (!ctx || !logits || !argmax_slots || !meta || !rng_state || !decision_out) return LADE_EINVAL;
-  if (!(temperature > 0.f) || vocab < 1 || ld < vocab) return LADE_EINVAL;
+  if (!(temperature > 0.f) || vocab < 1 || ld < vocab || top_k < 0 || !(top_p > 0.f) || top_p > 1.f) return LADE_EINVAL;
   if (ctx->d.D != 1) return LADE_ESTATE;                                   // no LP on the sampling path
   if (ctx->d.G > SMP_MAX_NGRAMS || ctx->d.GS > 64) return LADE_EUNSUPPORTED;
   sample_verify_kernel<<<1, SMP_THREADS, 0, (cudaStream_t)stream>>>(
-      ctx->state, ctx->d, (const __nv_bfloat16*)logits, ld, vocab, argmax_slots, meta, temperature,
+      ctx->state, ctx->d, (const __nv_bfloat16*)logits, ld, vocab, argmax_slots, meta, temperature, top_k, top_p,
       reinterpret_cast<unsigned long long*>(rng_state), decision_out, debug_uniforms);
   LADE_LAUNCH_CHECK("sample_verify_kernel");
   return LADE_OK;

@@ -216,7 +216,7 @@ class LookaheadEngine:
         self.dec_dev = torch.zeros(self.rec_ints + 4 + self.W, **i32)          # decision record of the sampling path
         if not hasattr(self, "rng_state"):
             self.rng_state = torch.zeros(2, dtype=torch.int64, device=dev)     # Philox (seed, offset), advanced on device
-            self.sample_temperature = 1.0
+            self.sample_temperature, self.sample_top_k, self.sample_top_p = 1.0, 0, 1.0
         self.lp_send = torch.zeros(self.rec_ints, **i32)
         self.lp_recv = torch.zeros(self.DW * self.rec_ints, **i32)
         self.h = torch.empty(rows, self.H, dtype=bf, device=dev)
@@ -345,7 +345,8 @@ class LookaheadEngine:
             return n
         if commit == "sample":      # verification + residual draw on device (Philox), then the state update
             check(lib.lade_sample_verify(self._ctx, stream, _ptr(self.logits), self.V, self.V, _ptr(self.am), _ptr(self.meta),
-                                         float(self.sample_temperature), _ptr(self.rng_state), _ptr(self.dec_dev),
+                                         float(self.sample_temperature), int(self.sample_top_k), float(self.sample_top_p),
+                                         _ptr(self.rng_state), _ptr(self.dec_dev),
                                          _ptr(getattr(self, "debug_uniforms", None))),
                   "lade_sample_verify")
             check(lib.lade_commit_decision(self._ctx, stream, _ptr(self.dec_dev), _ptr(self.meta), _ptr(self.res)),
@@ -463,7 +464,8 @@ class LookaheadEngine:
     def _steady_graph(self, commit: bool = True):
         if self._graph is None:
             self._graph = {}
-        key = (commit, float(self.sample_temperature)) if commit == "sample" else commit
+        key = (commit, float(self.sample_temperature), int(self.sample_top_k), float(self.sample_top_p)) \
+            if commit == "sample" else commit
         if key in self._graph:
             self._graph_n = self._graph[key][1]
             return self._graph[key][0]
@@ -532,7 +534,7 @@ class LookaheadEngine:
         """Greedy lookahead decoding; returns prompt + generated ids (trimmed to P + max_new_tokens).
         `stop_fn(ids) -> bool`: host-evaluated stopping criteria beyond max-length / EOS, checked after every step
         like lade/decoding.py:1215 (disables the one-step-deep host pipelining).
-        `sampling={"temperature": T, "seed": s}`: the sampling loop (jacobi_sample_multilevel, lade/decoding.py:137) with
+        `sampling={"temperature": T, "top_k": k, "top_p": p, "seed": s}`: the sampling loop (jacobi_sample_multilevel, lade/decoding.py:137) with
         the verification on device (lade_sample_verify, Philox stream seeded by `s`): same host loop, same CUDA graph
         replay per step, the only difference is the commit kernels at the end of the step."""
         prompt = [int(t) for t in prompt_ids]
@@ -547,7 +549,10 @@ class LookaheadEngine:
             T = float(sampling.get("temperature", 1.0))
             if not T > 0:
                 raise LadeError("temperature must be > 0")
-            self.sample_temperature = T
+            top_k, top_p = int(sampling.get("top_k", 0) or 0), float(sampling.get("top_p", 1.0))
+            if top_k < 0 or not 0.0 < top_p <= 1.0:
+                raise LadeError("top_k must be >= 0 and top_p in (0, 1]")
+            self.sample_temperature, self.sample_top_k, self.sample_top_p = T, top_k, top_p
             commit = "sample"
         self.begin(prompt, max_length, eos_token_ids, self.draw_window(prompt, rng, window0))
         if sampling is not None:

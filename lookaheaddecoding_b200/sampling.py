@@ -2,13 +2,13 @@
 
 Two ways to run the multi-candidate rejection-sampling verification (``decoding.py:484-540``, modified SpecInfer):
 
-* **device (default when the warpers are within {temperature})**: ``lade_sample_verify`` -- softmax, accept tests,
-  zero-and-renormalise, residual multinomial draw and the EOS window filter in one kernel driven by a Philox
-  stream -- followed by ``lade_commit_decision``; the whole step replays from one CUDA graph and the host loop is the
+* **device (default for the warper lists HF builds from temperature / top_k / top_p)**: ``lade_sample_verify`` --
+  temperature, top-k and top-p cut-offs, softmax, accept tests, zero-and-renormalise, residual multinomial draw and
+  the EOS window filter in one kernel driven by a Philox stream -- followed by ``lade_commit_decision``; the whole step replays from one CUDA graph and the host loop is the
   pipelined greedy loop (``LookaheadEngine.generate(..., sampling=...)``).  Same distribution as the reference, its own
   random stream (seeded from torch's global generator, so ``torch.manual_seed`` makes a run reproducible).
-* **host-RNG compatibility mode** (``sample_lookahead`` below; used for top-k / top-p warpers, or when
-  ``CONFIG_MAP["SAMPLING_ON_HOST"]`` is set): the model forward, window / pool / KV bookkeeping and row-wise argmax
+* **host-RNG compatibility mode** (``sample_lookahead`` below; used when ``CONFIG_MAP["SAMPLING_ON_HOST"]`` is set
+  or the warpers carry non-default filter values): the model forward, window / pool / KV bookkeeping and row-wise argmax
   run on the device; the verification runs here against device probability tensors, consuming python's
   ``random.random()`` for the accept tests and ``torch.multinomial`` for the residual draw in the reference's order,
   so that under fixed seeds the token stream follows the reference draw for draw (the fixed-seed golden tests).
@@ -47,15 +47,36 @@ def _check_warpers(logits_warper):
             raise LadeError(f"please set top_k=0.0 and top_p=1.0 {w}")                     # decoding.py:377
 
 
+def device_sampling_params(logits_warper):
+    """(temperature, top_k, top_p) when the warper list is what HF builds from generate(temperature=, top_k=, top_p=) --
+    at most one TemperatureLogitsWarper, TopKLogitsWarper, TopPLogitsWarper, in that order, -inf filter value,
+    min_tokens_to_keep = 1 -- i.e. what the device kernel implements; else None (host-RNG compatibility loop)."""
+    from transformers.generation.logits_process import TemperatureLogitsWarper, TopKLogitsWarper, TopPLogitsWarper
+    order = {TemperatureLogitsWarper: 0, TopKLogitsWarper: 1, TopPLogitsWarper: 2}
+    T, k, p, last = 1.0, 0, 1.0, -1
+    for w in list(logits_warper or []):
+        rank = order.get(type(w))
+        if rank is None or rank <= last:
+            return None
+        last = rank
+        if rank == 0:
+            T = float(w.temperature)
+        else:
+            if getattr(w, "filter_value", -float("inf")) != -float("inf") or getattr(w, "min_tokens_to_keep", 1) != 1:
+                return None
+            if rank == 1:
+                k = int(w.top_k)
+            else:
+                p = float(w.top_p)
+    if not T > 0 or k < 0 or not 0.0 < p <= 1.0:
+        return None
+    return T, k, p
+
+
 def device_temperature(logits_warper):
-    """T if the warper list is empty or a single TemperatureLogitsWarper (the set the device kernel implements), else None."""
-    from transformers.generation.logits_process import TemperatureLogitsWarper
-    ws = list(logits_warper or [])
-    if not ws:
-        return 1.0
-    if len(ws) == 1 and type(ws[0]) is TemperatureLogitsWarper:
-        return float(ws[0].temperature)
-    return None
+    """T if the warper list is empty or a single TemperatureLogitsWarper, else None (kept for callers of round 2's API)."""
+    params = device_sampling_params(logits_warper)
+    return params[0] if params is not None and params[1] == 0 and params[2] == 1.0 else None
 
 
 @torch.no_grad()
@@ -214,11 +235,12 @@ def jacobi_sample_multilevel(self, input_ids: torch.LongTensor, logits_processor
             CONFIG_MAP["DIST_WORKERS"] = saved
     from .decoding import _extra_stopping_criteria, _host_stop_fn
     stop_fn = _host_stop_fn(_extra_stopping_criteria(stopping_criteria), input_ids.device, input_ids.dtype)
-    temperature = device_temperature(logits_warper)
-    if temperature is not None and not CONFIG_MAP.get("SAMPLING_ON_HOST", 0):
+    params = device_sampling_params(logits_warper)
+    if params is not None and not CONFIG_MAP.get("SAMPLING_ON_HOST", 0):
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())          # reproducible under torch.manual_seed
         out = eng.generate(input_ids[0].tolist(), total - init_len, eos_token_ids=eos_token_id or (), rng=random,
-                           stop_fn=stop_fn, sampling={"temperature": temperature, "seed": seed})
+                           stop_fn=stop_fn, sampling={"temperature": params[0], "top_k": params[1], "top_p": params[2],
+                                                      "seed": seed})
     else:
         out = sample_lookahead(eng, input_ids[0].tolist(), total - init_len, logits_warper, eos_token_id or (), rng=random,
                                stop_fn=stop_fn)

@@ -14,15 +14,36 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 
-def softmax_T(row: np.ndarray, temperature: float) -> np.ndarray:
-    """softmax(row / T) in float64 from the fp32 scores the reference would form (:445,:485-489)."""
+def softmax_T(row: np.ndarray, temperature: float, top_k: int = 0, top_p: float = 1.0) -> np.ndarray:
+    """softmax of the warped scores in float64: TemperatureLogitsWarper (row / T, fp32), TopKLogitsWarper (keep every
+    score >= the k-th largest), TopPLogitsWarper (ascending cumulative probability of the filtered softmax: drop while
+    cum <= 1 - top_p, keep at least one) -- the warpers the reference admits (:375-377,:445,:485-489).  Scores of equal
+    value are kept or dropped together (torch.sort leaves their order, hence HF's cut inside such a group, undefined);
+    `tests/test_oracle_sampling_device.py` pins this function to the HF warpers on tie-free rows."""
     s = (row.astype(np.float32) / np.float32(temperature)).astype(np.float64)
-    e = np.exp(s - s.max())
+    keep = np.ones(s.shape, dtype=bool)
+    if top_k and top_k < s.size:
+        kth = np.sort(s)[-top_k]
+        keep &= s >= kth
+    e = np.where(keep, np.exp(s - s.max()), 0.0)
+    if top_p < 1.0:
+        lim = (1.0 - top_p) * e.sum()
+        vals = np.unique(s[keep])                        # ascending
+        cum = 0.0
+        thr = vals[-1]
+        for v in vals:
+            m = e[s == v].sum()
+            if not (cum + m <= lim):
+                thr = v
+                break
+            cum += m
+        keep &= s >= min(thr, vals[-1])
+        e = np.where(keep, e, 0.0)
     return e / e.sum()
 
 
 def verify_given_uniforms(out_row: np.ndarray, guess_rows: Optional[np.ndarray], guess_tokens: Optional[Sequence[int]], gs: int,
-                          temperature: float, uniforms: Sequence[float]):
+                          temperature: float, uniforms: Sequence[float], top_k: int = 0, top_p: float = 1.0):
     """Returns dict(hits, max_hit_idx, used, checks) where `checks` lists every comparison made:
     ("accept", u, p) or ("draw", u, probs) so that the caller can judge near-threshold cases."""
     it = iter(uniforms)
@@ -32,10 +53,10 @@ def verify_given_uniforms(out_row: np.ndarray, guess_rows: Optional[np.ndarray],
     used = 0
     if not guess_tokens:                                                                   # :458-480,:543-546
         u = next(it); used += 1
-        probs = softmax_T(out_row, temperature)
+        probs = softmax_T(out_row, temperature, top_k, top_p)
         checks.append(("draw", u, probs))
         return dict(hits=None, max_hit_idx=0, used=used, checks=checks, n_hits=1)
-    probs_next = softmax_T(out_row, temperature)
+    probs_next = softmax_T(out_row, temperature, top_k, top_p)
     n_ng = len(guess_tokens) // gs
     alive = list(range(n_ng))
     n_hits = 0
@@ -59,7 +80,7 @@ def verify_given_uniforms(out_row: np.ndarray, guess_rows: Optional[np.ndarray],
             if tot > 0:
                 probs_next = probs_next / tot
         if accepted:
-            probs_next = softmax_T(row, temperature)                                       # :530
+            probs_next = softmax_T(row, temperature, top_k, top_p)                         # :530
             n_hits = i + 1
             continue
         u = next(it); used += 1                                                            # :533

@@ -175,14 +175,23 @@ def test_extra_stopping_criteria_are_found_and_evaluated_on_the_host():
     assert stop([1, 2, 3]) is False and stop([1, 7, 3]) is True
 
 
-def test_device_sampling_is_chosen_for_temperature_only_warpers():
+def test_device_sampling_is_chosen_for_the_warpers_generate_builds():
     from transformers.generation.logits_process import (LogitsProcessorList, TemperatureLogitsWarper, TopKLogitsWarper,
                                                         TopPLogitsWarper)
-    from lookaheaddecoding_b200.sampling import device_temperature
+    from transformers.generation.logits_process import TypicalLogitsWarper
+    from lookaheaddecoding_b200.sampling import device_sampling_params, device_temperature
     assert device_temperature(None) == 1.0 and device_temperature(LogitsProcessorList()) == 1.0
     assert abs(device_temperature(LogitsProcessorList([TemperatureLogitsWarper(0.8)])) - 0.8) < 1e-9
     assert device_temperature(LogitsProcessorList([TemperatureLogitsWarper(0.8), TopKLogitsWarper(50)])) is None
-    assert device_temperature(LogitsProcessorList([TopPLogitsWarper(0.9)])) is None
+    assert device_sampling_params(None) == (1.0, 0, 1.0)
+    assert device_sampling_params(LogitsProcessorList([TemperatureLogitsWarper(0.7), TopKLogitsWarper(50),
+                                                       TopPLogitsWarper(0.9)])) == (0.7, 50, 0.9)
+    assert device_sampling_params(LogitsProcessorList([TopPLogitsWarper(0.9)])) == (1.0, 0, 0.9)
+    # not what generate() builds -> host-RNG compatibility loop: wrong order, other warpers, non-default keep / fill
+    assert device_sampling_params(LogitsProcessorList([TopPLogitsWarper(0.9), TopKLogitsWarper(50)])) is None
+    assert device_sampling_params(LogitsProcessorList([TypicalLogitsWarper(0.5)])) is None
+    assert device_sampling_params(LogitsProcessorList([TopPLogitsWarper(0.9, min_tokens_to_keep=2)])) is None
+    assert device_sampling_params(LogitsProcessorList([TopKLogitsWarper(50, filter_value=-1e4)])) is None
 
 
 def test_eval_harness_bookkeeping_matches_the_reference_summary():
@@ -224,5 +233,5 @@ def test_nccl_entry_points_degrade_without_a_communicator():
     assert lib.lade_nccl_available() in (0, 1)
     assert lib.lade_nccl_comm_destroy(None) == _cabi.LADE_EINVAL
     assert lib.lade_lp_exchange(None, None, None, None, None) == _cabi.LADE_EINVAL
-    assert lib.lade_sample_verify(None, None, None, 0, 0, None, None, C.c_float(1.0), None, None, None) == _cabi.LADE_EINVAL
+    assert lib.lade_sample_verify(None, None, None, 0, 0, None, None, C.c_float(1.0), 0, C.c_float(1.0), None, None, None) == _cabi.LADE_EINVAL
     assert lib.lade_l2_prefetch(None, None, 0, 1, 16) == _cabi.LADE_EINVAL
