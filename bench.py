@@ -59,6 +59,10 @@ def parse():
                     help="skip the AR series and the extra BASELINE configs (7B sampling, 13B, periodic-text weights)")
     ap.add_argument("--weights", default="random", choices=["random", "cyclic"],
                     help="cyclic: o_proj/down_proj zeroed -> periodic text, n-gram hits (see build_model)")
+    ap.add_argument("--lp-scale", action="store_true",
+                    help="lookahead parallelism with WINDOW_SIZE and GUESS_SET_SIZE multiplied by the number of ranks (each "
+                         "rank keeps about the single-GPU row count: the lookahead capacity grows with N, not the per-rank "
+                         "work); not the BASELINE config -- the line says so in config.workload")
     ap.add_argument("--ref-budget-s", type=float, default=240.0,
                     help="--impl reference: wall-clock bound of the timed steady steps")
     ap.add_argument("--no-reference-cuda", action="store_true",
@@ -512,6 +516,8 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.lp_scale and world > 1:
+        W, G = W * world, G * world
     config = {"workload": f"{WORKLOAD_NAMES[args.workload]}, W={W} N={N} G={G}, prompt {P} tokens, {args.max_new} new tokens "
                           f"per generate()", "prompt_len": P, "max_new_tokens": args.max_new,
               "weights": "random-init normal(0, 0.02)" if args.weights == "random" else
