@@ -5,7 +5,43 @@
 // All are HBM-bound byte movers: 16-byte vectorised, coalesced, one pass over the data.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace lade {
+
+// Programmatic dependent launch on the glue kernels: every kernel orders itself behind its stream predecessor with
+// griddepcontrol.wait as its first instruction (so it is correct whatever the predecessor does) and then lets ITS
+// dependent start launching at once.  Whether a neighbouring library GEMM takes part is up to the library (a kernel
+// launched without the attribute, or one that never triggers, simply behaves like a normal stream-ordered launch).
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+static bool pdl_glue_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LADE_PDL_GLUE");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+// kernel launch with cudaLaunchAttributeProgrammaticStreamSerialization (when enabled)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_glue_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -23,6 +59,7 @@ __global__ void __launch_bounds__(1024) rmsnorm_kernel(const __nv_bfloat16* __re
                                                       __nv_bfloat16* __restrict__ out, int hidden, float eps) {
   extern __shared__ float s_row[];  // hidden floats
   __shared__ float s_part[32];
+  pdl_enter();
   const int out_row = blockIdx.x;
   const int in_row = GATHER ? rows_idx[out_row] : out_row;
   const __nv_bfloat16* xr = x + (long long)in_row * hidden;
@@ -83,7 +120,7 @@ __global__ void __launch_bounds__(1024) rope_append_kernel(
     int q_pad, int n_heads, int n_kv_heads, int D, int kv_capacity, int max_pos) {
   // programmatic dependent launch: let the consumer (lade_attn_fwd) start its prologue and prefetch the cache tiles of
   // earlier steps while this grid runs; it orders itself with griddepcontrol.wait before touching what is written here
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  pdl_enter();
   const int r = blockIdx.x;
   const int half = D >> 1;
   const int per_head = half >> 3;                        // 16-byte slices per half head
@@ -140,6 +177,7 @@ __global__ void __launch_bounds__(1024) rope_append_kernel(
 
 __global__ void swiglu_kernel(const __nv_bfloat16* __restrict__ gate_up, __nv_bfloat16* __restrict__ out,
                               int rows, int inter) {
+  pdl_enter();
   const int nvec = inter / 8;
   const long long total = (long long)rows * nvec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -208,10 +246,9 @@ int lade_rmsnorm(void* stream, const void* x, const void* delta, const void* wei
     LADE_CUDA_CHECK(cudaFuncSetAttribute(rmsnorm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // one 16-byte vector per thread when the row fits (4096 / 8 = 512 threads): a single round of loads per phase
   const int threads = norm_threads(hidden);
-  rmsnorm_kernel<false><<<rows, threads, smem, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, (const __nv_bfloat16*)delta, (const __nv_bfloat16*)weight, nullptr,
-      (__nv_bfloat16*)h_out, (__nv_bfloat16*)out, hidden, eps);
-  LADE_LAUNCH_CHECK("rmsnorm_kernel");
+  LADE_CUDA_CHECK(launch_pdl(rmsnorm_kernel<false>, dim3(rows), dim3(threads), smem, (cudaStream_t)stream,
+                             (const __nv_bfloat16*)x, (const __nv_bfloat16*)delta, (const __nv_bfloat16*)weight,
+                             (const int*)nullptr, (__nv_bfloat16*)h_out, (__nv_bfloat16*)out, hidden, eps));
   return LADE_OK;
 }
 
@@ -223,10 +260,9 @@ int lade_rmsnorm_gather(void* stream, const void* x, const void* delta, const vo
   if (smem > 48 * 1024)
     LADE_CUDA_CHECK(cudaFuncSetAttribute(rmsnorm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int threads = norm_threads(hidden);
-  rmsnorm_kernel<true><<<n_rows, threads, smem, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, (const __nv_bfloat16*)delta, (const __nv_bfloat16*)weight, rows_idx, nullptr,
-      (__nv_bfloat16*)out, hidden, eps);
-  LADE_LAUNCH_CHECK("rmsnorm_gather_kernel");
+  LADE_CUDA_CHECK(launch_pdl(rmsnorm_kernel<true>, dim3(n_rows), dim3(threads), smem, (cudaStream_t)stream,
+                             (const __nv_bfloat16*)x, (const __nv_bfloat16*)delta, (const __nv_bfloat16*)weight,
+                             (const int*)rows_idx, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)out, hidden, eps));
   return LADE_OK;
 }
 
@@ -239,11 +275,10 @@ int lade_rope_append(void* stream, const void* qkv, const void* cos_tab, const v
   // one work item (head, 8-wide slice) per thread when they fit: (32 + 2*32) heads * 8 slices = 768 threads at 7B
   int rope_threads = (((n_heads + 2 * n_kv_heads) * (head_dim / 16) + 31) / 32) * 32;
   rope_threads = rope_threads < 128 ? 128 : (rope_threads > 1024 ? 1024 : rope_threads);
-  rope_append_kernel<<<rows, rope_threads, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)cos_tab, (const __nv_bfloat16*)sin_tab, pos, meta,
-      (__nv_bfloat16*)q_out, (__nv_bfloat16*)k_cache, (__nv_bfloat16*)v_cache, q_pad, n_heads, n_kv_heads,
-      head_dim, kv_capacity, max_pos);
-  LADE_LAUNCH_CHECK("rope_append_kernel");
+  LADE_CUDA_CHECK(launch_pdl(rope_append_kernel, dim3(rows), dim3(rope_threads), 0, (cudaStream_t)stream,
+                             (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)cos_tab, (const __nv_bfloat16*)sin_tab,
+                             (const int*)pos, (const int*)meta, (__nv_bfloat16*)q_out, (__nv_bfloat16*)k_cache,
+                             (__nv_bfloat16*)v_cache, q_pad, n_heads, n_kv_heads, head_dim, kv_capacity, max_pos));
   return LADE_OK;
 }
 
@@ -252,8 +287,8 @@ int lade_swiglu(void* stream, const void* gate_up, void* out, int32_t rows, int3
   const long long total = (long long)rows * (inter / 8);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  swiglu_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)gate_up, (__nv_bfloat16*)out, rows, inter);
-  LADE_LAUNCH_CHECK("swiglu_kernel");
+  LADE_CUDA_CHECK(launch_pdl(swiglu_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream,
+                             (const __nv_bfloat16*)gate_up, (__nv_bfloat16*)out, rows, inter));
   return LADE_OK;
 }
 
