@@ -254,28 +254,38 @@ def attn_roofline(eng, shape, reps=5):
                                           attn_out.data_ptr(), rowmask.data_ptr(), mw, meta.data_ptr(),
                                           scratch.data_ptr(), rows, eng.nh, eng.nkv, eng.D, eng.kv_capacity,
                                           eng.kv_capacity, eng.attn_splits, eng.attn_impl))
-    for _ in range(3):
-        one_pass()
-    torch.cuda.synchronize()
-    # one pass over the L layer caches captured in a CUDA graph (the launch rate of a python loop, ~20 us per
-    # ctypes call, must not bound the kernel measurement); events on the replaying stream
-    g = torch.cuda.CUDAGraph()
-    side = torch.cuda.Stream(device=eng.dev)
-    side.wait_stream(torch.cuda.current_stream(eng.dev))
-    with torch.cuda.stream(side):
-        with torch.cuda.graph(g, stream=side):
+    def timed_us(pdl):
+        """us per launch, one pass over the L layer caches captured in a CUDA graph (the launch rate of a python loop,
+        ~20 us per ctypes call, must not bound the kernel measurement); events on the replaying stream."""
+        _cabi.check(lib.lade_debug_attn_pdl(pdl))
+        for _ in range(3):
             one_pass()
-    torch.cuda.current_stream(eng.dev).wait_stream(side)
-    g.replay()
-    torch.cuda.synchronize()
-    stream = torch.cuda.current_stream(eng.dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(reps):
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=eng.dev)
+        side.wait_stream(torch.cuda.current_stream(eng.dev))
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                one_pass()
+        torch.cuda.current_stream(eng.dev).wait_stream(side)
         g.replay()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) * 1e3 / (reps * eng.L)
+        torch.cuda.synchronize()
+        stream = torch.cuda.current_stream(eng.dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            g.replay()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / (reps * eng.L)
+
+    # (1) as launched in the decode step: programmatic dependent launch on -- there the kernel's set-up overlaps the
+    # tail of lade_rope_append; in this loop the predecessor is the previous layer's lade_attn_fwd, which triggers its
+    # dependents at entry in the same way (tools/step_ablation.py: the kernel costs the same 15 us inside the step);
+    # (2) strictly serialised launches (attribute off), reported beside it
+    us = timed_us(1)
+    us_serial = timed_us(0)
+    _cabi.check(lib.lade_debug_attn_pdl(-1))
     # algorithmic bytes per launch (SURVEY.md 8d): K,V cache read + Q read + new K,V read + O write
     Hq, Hkv, D = eng.nh, eng.nkv, eng.D
     bytes_alg = 2 * kv_len * Hkv * D * 2 + q_len * Hq * D * 2 + 2 * q_len * Hkv * D * 2 + q_len * Hq * D * 2
@@ -293,6 +303,9 @@ def attn_roofline(eng, shape, reps=5):
         traffic = None
     return {"bound": "hbm", "kernel": "lade_attn_fwd", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
             "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": how, "us_per_launch": round(us, 2),
+            "us_per_launch_serialized": round(us_serial, 2), "frac_serialized": round(bytes_alg / (us_serial * 1e-6) / 1e9 / peak, 4),
+            "launch_mode": "programmatic dependent launch as in the decode step (set-up overlaps the predecessor's tail); "
+                           "'serialized' = the same loop with the attribute off",
             "alg_bytes_per_launch": bytes_alg, "kv_len": kv_len, "q_len": q_len, "launches_timed": reps * eng.L}
 
 

@@ -173,6 +173,12 @@ int64_t lade_attn_scratch_bytes(int32_t q_pad, int32_t n_heads, int32_t head_dim
  * siblings arrived, merged, end). */
 int lade_debug_attn_timing(void* dev_buffer);
 
+/* Measurement aid: force the programmatic-dependent-launch attribute of lade_attn_fwd on (1) / off (0), or back to the
+ * environment default (-1, LADE_PDL).  With it on, a launch that follows a kernel which triggers its dependents early
+ * (lade_rope_append in the decode step; another lade_attn_fwd in a back-to-back loop) overlaps its set-up with the
+ * predecessor's tail; bench.py reports the kernel both ways. */
+int lade_debug_attn_pdl(int32_t enable);
+
 /* Projection GEMM of the lookahead step: c[m][n] (row stride ldc) = a[m][k] . w[n][k]^T, bf16 in/out, fp32
  * accumulation on tcgen05 tensor cores; w is an nn.Linear weight ([out_features][in_features], row-major).
  * Replaces q/k/v_proj (modeling_llama.py:447-449), o_proj (:541), gate/up/down_proj (:378) and lm_head (:1608)

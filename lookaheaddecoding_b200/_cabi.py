@@ -47,6 +47,7 @@ _SIGNATURES = {
     "lade_attn_fwd": (C.c_int, [c_p, c_p, c_p, c_p, c_p, c_p, c_i32, c_p, c_p] + [c_i32] * 8),
     "lade_attn_scratch_bytes": (C.c_int64, [c_i32, c_i32, c_i32, c_i32]),
     "lade_debug_attn_timing": (C.c_int, [c_p]),
+    "lade_debug_attn_pdl": (C.c_int, [c_i32]),
     "lade_gemm_bf16": (C.c_int, [c_p, c_p, c_p, c_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32]),
     "lade_debug_gemm_timing": (C.c_int, [c_p]),
     "lade_swiglu": (C.c_int, [c_p, c_p, c_p, c_i32, c_i32]),

@@ -9,11 +9,14 @@ int attn_fwd_tc_launch(cudaStream_t stream, const void* q, const void* k_cache, 
                        const uint32_t* rowmask, int mask_words, const int32_t* meta, void* scratch, int q_pad, int n_heads,
                        int n_kv_heads, int head_dim, int kv_capacity, int kv_bound, int n_splits);
 int attn_tc_set_timing_buffer(void* dev_ptr);
+int attn_tc_set_pdl(int v);
 }  // namespace lade
 
 extern "C" {
 
 int lade_debug_attn_timing(void* dev_buffer) { return lade::attn_tc_set_timing_buffer(dev_buffer); }
+
+int lade_debug_attn_pdl(int32_t enable) { return lade::attn_tc_set_pdl(enable); }
 
 
 int64_t lade_attn_scratch_bytes(int32_t q_pad, int32_t n_heads, int32_t head_dim, int32_t n_splits) {

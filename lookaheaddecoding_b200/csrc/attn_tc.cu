@@ -580,7 +580,11 @@ static int merge_mode() {          // default: DSMEM push (1); LADE_ATTN_MERGE=l
   return v;
 }
 
+static int g_pdl_override = -1;      // lade_debug_attn_pdl: -1 = environment (LADE_PDL), 0 / 1 = forced
+int attn_tc_set_pdl(int v) { g_pdl_override = v < 0 ? -1 : (v ? 1 : 0); return LADE_OK; }
+
 static bool pdl_enabled() {
+  if (g_pdl_override >= 0) return g_pdl_override != 0;
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("LADE_PDL");
