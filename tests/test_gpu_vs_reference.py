@@ -30,6 +30,8 @@ CASES = [("cfg1_w5n3g3",       TINY, 5,  3, 3,  64, 96, False),
          ("w15n5g15_pool",     TINY, 15, 5, 15, 64, 128, True),
          ("w20n7g20_pool",     TINY, 20, 7, 20, 96, 96, True),
          ("gqa_w15n5g15",      GQA,  15, 5, 15, 48, 96, False),
+         # a summarisation-length prompt: 21 query tiles of prefill attention, kv past 2.5 k in the decode steps
+         ("long_prompt_2600",  dict(TINY, max_pos=4096), 15, 5, 15, 2600, 48, True),
          # edge shapes (tests/golden/gen_golden_edge.py)
          ("edge_p1",           TINY, 5,  3, 3,  1,  24, True),
          ("edge_p2_lt_n",      TINY, 7,  5, 7,  2,  24, True),
