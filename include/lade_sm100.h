@@ -159,7 +159,9 @@ int lade_rope_append(void* stream, const void* qkv, const void* cos_tab, const v
  * lookahead mask) V with the mask bits of `rowmask` tested in registers (prefill steps: plain causal,
  * rowmask unused); all step rows see the committed cache.  Replaces LlamaAttention.forward's attention core (modeling_llama.py:520-541), the
  * dense mask of j_make_causal_mask_multilevel (:115-207) and flash_attn_lade.flash_attn_func(...,
- * lookahead=[...]) (:705-713).  `scratch` holds split-KV partials: lade_attn_scratch_bytes(). */
+ * lookahead=[...]) (:705-713).  `scratch` holds split-KV partials: lade_attn_scratch_bytes().
+ * head_dim 128: tcgen05/TMA kernel (impl 0 or 2) or the mma.sync kernel (impl 1); head_dim 64 (TinyLlama-style): the
+ * mma.sync kernel (impl 0 or 1).  Other head dimensions: LADE_EUNSUPPORTED. */
 int lade_attn_fwd(void* stream, const void* q, const void* k_cache, const void* v_cache, void* out,
                   const uint32_t* rowmask, int32_t mask_words, const int32_t* meta, void* scratch, int32_t q_pad,
                   int32_t n_heads, int32_t n_kv_heads, int32_t head_dim, int32_t kv_capacity,

@@ -33,7 +33,9 @@ int lade_attn_fwd(void* stream, const void* q, const void* k_cache, const void* 
   if (rowmask && mask_words * 32 < q_pad) return LADE_EINVAL;   // rowmask may be NULL for prefill-only use
   if (q_pad < 1 || n_heads < 1 || n_kv_heads < 1 || n_heads % n_kv_heads != 0 || n_splits < 1 || kv_capacity < 1)
     return LADE_EINVAL;
-  if (impl == 0 || impl == 2)   // default: the Blackwell-native tcgen05/TMA kernel
+  // impl 0 = the library's choice: the Blackwell-native tcgen05/TMA kernel for head_dim 128, the mma.sync kernel for the
+  // other instantiated head dimension (64); impl 2 / 1 force one of them
+  if ((impl == 0 && head_dim == 128) || impl == 2)
     return lade::attn_fwd_tc_launch((cudaStream_t)stream, q, k_cache, v_cache, out, rowmask, mask_words, meta, scratch, q_pad,
                                     n_heads, n_kv_heads, head_dim, kv_capacity, kv_bound, n_splits);
   return lade::attn_fwd_mma_launch((cudaStream_t)stream, q, k_cache, v_cache, out, rowmask, mask_words, meta, scratch, q_pad,

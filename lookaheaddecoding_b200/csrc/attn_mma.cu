@@ -6,6 +6,9 @@
 // LlamaAttention.forward (lade/models/modeling_llama.py:520-541) + the dense additive mask of
 // j_make_causal_mask_multilevel (:115-207).
 //
+// Head dimensions 128 (Llama-2/3, CodeLlama) and 64 (TinyLlama-style) are instantiated; the tcgen05 path is built for
+// 128 only, so 64 always runs here.
+//
 // Rounding points follow the reference: scores = bf16(QK^T) ; bf16(scores * (1/sqrt(D))) (torch's
 // CUDA division-by-scalar multiplies by the fp32 reciprocal) ; fp32 softmax ; bf16 probabilities ;
 // fp32-accumulated PV ; bf16 output.
@@ -13,7 +16,6 @@
 
 namespace lade {
 
-constexpr int ATT_D = 128;
 constexpr int ATT_BM = 128;
 constexpr int ATT_BN = 64;
 constexpr int ATT_STAGES = 3;
@@ -49,24 +51,28 @@ __device__ __forceinline__ unsigned pack_bf16(float lo, float hi) {
   return *reinterpret_cast<unsigned*>(&v);
 }
 
-// swizzled element offset inside a [BN][128] bf16 tile: 16-byte chunk index XOR (row & 7)
+// swizzled element offset inside a [BN][ATT_D] bf16 tile: 16-byte chunk index XOR (row & 7)
+template <int ATT_D>
 __device__ __forceinline__ int swz(int row, int chunk) { return row * ATT_D + ((chunk ^ (row & 7)) << 3); }
 
+template <int ATT_D>
 __device__ __forceinline__ void load_tile_async(__nv_bfloat16* sK, __nv_bfloat16* sV, const __nv_bfloat16* gK,
                                                 const __nv_bfloat16* gV, int row0, int T, int kv_capacity) {
-  // 64 rows x 16 chunks = 1024 chunks per tensor; 256 threads -> 4 chunks each per tensor
+  // 64 rows x (ATT_D / 8) 16-byte chunks per tensor; 256 threads -> 4 (D = 128) or 2 (D = 64) chunks each per tensor
+  constexpr int CPR = ATT_D / 8;
 #pragma unroll
-  for (int i = 0; i < (ATT_BN * 16) / ATT_THREADS; ++i) {
+  for (int i = 0; i < (ATT_BN * CPR) / ATT_THREADS; ++i) {
     const int c = threadIdx.x + i * ATT_THREADS;
-    const int row = c >> 4, chunk = c & 15;
+    const int row = c / CPR, chunk = c % CPR;
     const int grow = row0 + row;
     const int ok = (grow < T) ? 16 : 0;
     const int crow = grow < kv_capacity ? grow : kv_capacity - 1;
-    cp_async16(sK + swz(row, chunk), gK + (long long)crow * ATT_D + chunk * 8, ok);
-    cp_async16(sV + swz(row, chunk), gV + (long long)crow * ATT_D + chunk * 8, ok);
+    cp_async16(sK + swz<ATT_D>(row, chunk), gK + (long long)crow * ATT_D + chunk * 8, ok);
+    cp_async16(sV + swz<ATT_D>(row, chunk), gV + (long long)crow * ATT_D + chunk * 8, ok);
   }
 }
 
+template <int ATT_D>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k_cache,
                     const __nv_bfloat16* __restrict__ v_cache, __nv_bfloat16* __restrict__ out,
@@ -107,18 +113,20 @@ attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
 #pragma unroll
   for (int s = 0; s < ATT_STAGES - 1; ++s) {
     if (s < my_tiles)
-      load_tile_async(sK + s * ATT_BN * ATT_D, sV + s * ATT_BN * ATT_D, gK, gV, (tile_lo + s) * ATT_BN, T, kv_capacity);
+      load_tile_async<ATT_D>(sK + s * ATT_BN * ATT_D, sV + s * ATT_BN * ATT_D, gK, gV, (tile_lo + s) * ATT_BN, T, kv_capacity);
     cp_async_commit();
   }
 
   // Q fragments (A operand), 16 rows per warp
   const int row_a = mt * ATT_BM + warp * 16 + (lane >> 2);  // step-local row of c0/c1
   const int row_b = row_a + 8;
-  unsigned qf[8][4];
+  constexpr int KK = ATT_D / 16;       // k16 steps of QK^T
+  constexpr int ND = ATT_D / 8;        // 8-wide n-tiles of the output
+  unsigned qf[KK][4];
   {
     const __nv_bfloat16* qh = q + (long long)h * q_pad * ATT_D;
 #pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
+    for (int kk = 0; kk < KK; ++kk) {
       const int col = kk * 16 + (lane & 3) * 2;
       qf[kk][0] = row_a < q_pad ? *reinterpret_cast<const unsigned*>(qh + (long long)row_a * ATT_D + col) : 0u;
       qf[kk][1] = row_b < q_pad ? *reinterpret_cast<const unsigned*>(qh + (long long)row_b * ATT_D + col) : 0u;
@@ -130,9 +138,9 @@ attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
   const uint32_t* mrow_a = (have_mask && row_a < q_pad) ? rowmask + (long long)row_a * mask_words : nullptr;
   const uint32_t* mrow_b = (have_mask && row_b < q_pad) ? rowmask + (long long)row_b * mask_words : nullptr;
 
-  float o_acc[16][4];
+  float o_acc[ND][4];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) { o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f; }
+  for (int i = 0; i < ND; ++i) { o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f; }
   float m_a = -INFINITY, m_b = -INFINITY, l_a = 0.f, l_b = 0.f;
   const float LOG2E = 1.4426950408889634f;
 
@@ -142,7 +150,7 @@ attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
       const int nt = it + ATT_STAGES - 1;
       if (nt < my_tiles) {
         const int st = nt % ATT_STAGES;
-        load_tile_async(sK + st * ATT_BN * ATT_D, sV + st * ATT_BN * ATT_D, gK, gV, (tile_lo + nt) * ATT_BN, T, kv_capacity);
+        load_tile_async<ATT_D>(sK + st * ATT_BN * ATT_D, sV + st * ATT_BN * ATT_D, gK, gV, (tile_lo + nt) * ATT_BN, T, kv_capacity);
       }
       cp_async_commit();
     }
@@ -158,14 +166,14 @@ attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s_acc[i][0] = s_acc[i][1] = s_acc[i][2] = s_acc[i][3] = 0.f; }
 #pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
+    for (int kk = 0; kk < KK; ++kk) {
 #pragma unroll
       for (int np = 0; np < 4; ++np) {  // pairs of n-tiles
         unsigned b0, b1, b2, b3;
         const int m = lane >> 3, r = lane & 7;
         const int row = np * 16 + (m >> 1) * 8 + r;
         const int chunk = kk * 2 + (m & 1);
-        ldmatrix_x4(b0, b1, b2, b3, tK + swz(row, chunk));
+        ldmatrix_x4(b0, b1, b2, b3, tK + swz<ATT_D>(row, chunk));
         mma_bf16(s_acc[np * 2], qf[kk], b0, b1);
         mma_bf16(s_acc[np * 2 + 1], qf[kk], b2, b3);
       }
@@ -221,7 +229,7 @@ attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
     l_a = l_a * sc_a + ps_a;
     l_b = l_b * sc_b + ps_b;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
+    for (int i = 0; i < ND; ++i) {
       o_acc[i][0] *= sc_a; o_acc[i][1] *= sc_a; o_acc[i][2] *= sc_b; o_acc[i][3] *= sc_b;
     }
 
@@ -229,12 +237,12 @@ attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
-      for (int nd = 0; nd < 8; ++nd) {  // pairs of d n-tiles
+      for (int nd = 0; nd < ND / 2; ++nd) {  // pairs of d n-tiles
         unsigned b0, b1, b2, b3;
         const int m = lane >> 3, r = lane & 7;
         const int row = ks * 16 + (m & 1) * 8 + r;
         const int chunk = nd * 2 + (m >> 1);
-        ldmatrix_x4_trans(b0, b1, b2, b3, tV + swz(row, chunk));
+        ldmatrix_x4_trans(b0, b1, b2, b3, tV + swz<ATT_D>(row, chunk));
         mma_bf16(o_acc[nd * 2], pf[ks], b0, b1);
         mma_bf16(o_acc[nd * 2 + 1], pf[ks], b2, b3);
       }
@@ -254,7 +262,7 @@ attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
     const float inv_a = l_a > 0.f ? 1.f / l_a : 0.f;
     const float inv_b = l_b > 0.f ? 1.f / l_b : 0.f;
 #pragma unroll
-    for (int nt = 0; nt < 16; ++nt) {
+    for (int nt = 0; nt < ND; ++nt) {
       const int col = nt * 8 + (lane & 3) * 2;
       if (row_a < q_pad)
         *reinterpret_cast<unsigned*>(out + (long long)row_a * HD + h * ATT_D + col) = pack_bf16(o_acc[nt][0] * inv_a, o_acc[nt][1] * inv_a);
@@ -270,7 +278,7 @@ attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
     float* po = part_o + (((long long)split * n_heads + h) * rows_pad) * ATT_D;
     float* pml = part_ml + (((long long)split * n_heads + h) * rows_pad) * 2;
 #pragma unroll
-    for (int nt = 0; nt < 16; ++nt) {
+    for (int nt = 0; nt < ND; ++nt) {
       const int col = nt * 8 + (lane & 3) * 2;
       *reinterpret_cast<float2*>(po + (long long)row_a * ATT_D + col) = make_float2(o_acc[nt][0], o_acc[nt][1]);
       *reinterpret_cast<float2*>(po + (long long)row_b * ATT_D + col) = make_float2(o_acc[nt][2], o_acc[nt][3]);
@@ -317,17 +325,17 @@ attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
   if (threadIdx.x == 0) counters[h * q_tiles + mt] = 0;
 }
 
-int attn_fwd_mma_launch(cudaStream_t stream, const void* q, const void* k_cache, const void* v_cache, void* out,
-                        const uint32_t* rowmask, int mask_words, const int32_t* meta, void* scratch, int q_pad, int n_heads,
-                        int n_kv_heads, int head_dim, int kv_capacity, int n_splits) {
-  if (head_dim != ATT_D) return LADE_EUNSUPPORTED;
+template <int ATT_D>
+static int attn_fwd_mma_launch_d(cudaStream_t stream, const void* q, const void* k_cache, const void* v_cache, void* out,
+                                 const uint32_t* rowmask, int mask_words, const int32_t* meta, void* scratch, int q_pad,
+                                 int n_heads, int n_kv_heads, int kv_capacity, int n_splits) {
   const int q_tiles = (q_pad + ATT_BM - 1) / ATT_BM;
   const size_t smem = (size_t)2 * ATT_STAGES * ATT_BN * ATT_D * sizeof(__nv_bfloat16);
   static unsigned long long attr_devs = 0;   // the attribute is per device (context): one bit per ordinal
   int cur_dev = 0;
   LADE_CUDA_CHECK(cudaGetDevice(&cur_dev));
   if (!((attr_devs >> (cur_dev & 63)) & 1ull)) {
-    LADE_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LADE_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_mma_kernel<ATT_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_devs |= 1ull << (cur_dev & 63);
   }
   const long long rows_pad = (long long)q_tiles * ATT_BM;
@@ -337,12 +345,24 @@ int attn_fwd_mma_launch(cudaStream_t stream, const void* q, const void* k_cache,
   float* part_ml = reinterpret_cast<float*>(counters + ATTN_MAX_COUNTERS);
   float* part_o = part_ml + (long long)n_splits * n_heads * rows_pad * 2;
   dim3 grid(n_splits, n_heads, q_tiles);
-  attn_fwd_mma_kernel<<<grid, ATT_THREADS, smem, stream>>>(
+  attn_fwd_mma_kernel<ATT_D><<<grid, ATT_THREADS, smem, stream>>>(
       (const __nv_bfloat16*)q, (const __nv_bfloat16*)k_cache, (const __nv_bfloat16*)v_cache, (__nv_bfloat16*)out,
       rowmask, mask_words, meta, part_o, part_ml, counters, q_pad, n_heads, n_kv_heads, kv_capacity, n_splits,
-      1.0f / sqrtf((float)head_dim));
+      1.0f / sqrtf((float)ATT_D));
   LADE_LAUNCH_CHECK("attn_fwd_mma_kernel");
   return LADE_OK;
+}
+
+int attn_fwd_mma_launch(cudaStream_t stream, const void* q, const void* k_cache, const void* v_cache, void* out,
+                        const uint32_t* rowmask, int mask_words, const int32_t* meta, void* scratch, int q_pad, int n_heads,
+                        int n_kv_heads, int head_dim, int kv_capacity, int n_splits) {
+  if (head_dim == 128)
+    return attn_fwd_mma_launch_d<128>(stream, q, k_cache, v_cache, out, rowmask, mask_words, meta, scratch, q_pad, n_heads,
+                                      n_kv_heads, kv_capacity, n_splits);
+  if (head_dim == 64)
+    return attn_fwd_mma_launch_d<64>(stream, q, k_cache, v_cache, out, rowmask, mask_words, meta, scratch, q_pad, n_heads,
+                                     n_kv_heads, kv_capacity, n_splits);
+  return LADE_EUNSUPPORTED;
 }
 
 }  // namespace lade

@@ -95,8 +95,8 @@ class LookaheadEngine:
         self.I = cfg.intermediate_size
         self.V = cfg.vocab_size
         self.eps = float(cfg.rms_norm_eps)
-        if self.D != 128:
-            raise LadeError(f"head_dim {self.D} unsupported (the sm_100a attention kernel is built for 128)")
+        if self.D not in (64, 128):
+            raise LadeError(f"head_dim {self.D} unsupported (attention kernels are instantiated for 128 and 64)")
         self.max_pos = int(getattr(cfg, "max_position_embeddings", 4096))
         rp = getattr(cfg, "rope_parameters", None) or {}
         self.rope_theta = float(rp.get("rope_theta", getattr(cfg, "rope_theta", 10000.0)) if isinstance(rp, dict)

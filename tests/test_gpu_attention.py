@@ -148,3 +148,27 @@ def test_attention_lp_shapes_vs_oracle(impl):
         v = torch.randn(Hq, T, 128, device="cuda").to(torch.bfloat16)
         out = run_kernel(q, k, v, lay, meta_for(lay, kv_len, lay.q_len), lay.q_len, 2, impl)
         check_close(out, _oracle_attn(q, k, v, lay, kv_len))
+
+
+@pytest.mark.parametrize("kv_len,Hq,Hkv,splits", [(0, 4, 4, 1), (77, 4, 2, 3), (700, 8, 2, 4)])
+def test_attention_head_dim_64_vs_oracle(kv_len, Hq, Hkv, splits):
+    """head_dim 64 (TinyLlama-style): served by the mma.sync kernel (impl 0 picks it; the tcgen05 kernel is 128-only)."""
+    torch.manual_seed(kv_len + 64)
+    W, N, g = 15, 5, 7
+    gs = N - 1
+    lay = LA.layout_from_shape([W - 1] + [W] * (N - 2), 1, g * gs, gs)
+    q_len, D = lay.q_len, 64
+    T = kv_len + q_len
+    q = torch.randn(Hq, q_len, D, device="cuda").to(torch.bfloat16)
+    k = torch.randn(Hkv, T, D, device="cuda").to(torch.bfloat16)
+    v = torch.randn(Hkv, T, D, device="cuda").to(torch.bfloat16)
+    q_pad = gs * (W + g) + 4
+    for impl in (0, 1):
+        out = run_kernel(q, k, v, lay, meta_for(lay, kv_len, q_pad), q_pad, splits, impl)
+        check_close(out, _oracle_attn(q, k, v, lay, kv_len))
+    from lookaheaddecoding_b200 import _cabi
+    lib = _cabi.load()
+    z = torch.zeros(64, device="cuda")
+    rc = lib.lade_attn_fwd(0, z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), 0, 0, z.data_ptr(), z.data_ptr(), 8, 2, 2, 64,
+                           16, 16, 1, 2)
+    assert rc == _cabi.LADE_EUNSUPPORTED          # the tcgen05 kernel refuses head_dim 64 when forced

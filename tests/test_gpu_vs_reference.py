@@ -22,6 +22,8 @@ pytestmark = [pytest.mark.gpu,
 
 TINY = dict(hidden=256, layers=2, heads=2, kv_heads=2, inter=688, vocab=32000, max_pos=2048, rope_theta=10000.0, eps=1e-5)
 GQA = dict(hidden=512, layers=2, heads=4, kv_heads=2, inter=688, vocab=4096, max_pos=2048, rope_theta=10000.0, eps=1e-5)
+# head_dim 64 with grouped KV heads: the TinyLlama-1.1B layout (2048 / 32 heads, 4 KV heads) in miniature
+D64 = dict(hidden=256, layers=2, heads=4, kv_heads=2, inter=688, vocab=4096, max_pos=2048, rope_theta=10000.0, eps=1e-5)
 
 #        name                 shape  W   N  G   P  new pool
 CASES = [("cfg1_w5n3g3",       TINY, 5,  3, 3,  64, 96, False),
@@ -30,6 +32,7 @@ CASES = [("cfg1_w5n3g3",       TINY, 5,  3, 3,  64, 96, False),
          ("w15n5g15_pool",     TINY, 15, 5, 15, 64, 128, True),
          ("w20n7g20_pool",     TINY, 20, 7, 20, 96, 96, True),
          ("gqa_w15n5g15",      GQA,  15, 5, 15, 48, 96, False),
+         ("d64_gqa_w15n5g15",  D64,  15, 5, 15, 48, 96, True),
          # a summarisation-length prompt: 21 query tiles of prefill attention, kv past 2.5 k in the decode steps
          ("long_prompt_2600",  dict(TINY, max_pos=4096), 15, 5, 15, 2600, 48, True),
          # edge shapes (tests/golden/gen_golden_edge.py)
