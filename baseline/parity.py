@@ -12,7 +12,7 @@ positions).  So the check is:
   * compare ids position by position;
   * at a divergence, compute the reference model's OWN next-token logits on the common prefix (its plain causal
     forward, ``LlamaModeljforward(is_prefill=True)``, ``modeling_llama.py:1108``) and record the margin between the two
-    candidates and the top logit, in bf16 ulps of the top logit;
+    candidates and the top logit, in ulps of the model dtype (bf16, or fp16 for fp16 models) at the top logit;
   * force the reference's token (re-run ours from ``ref[:i+1]``) and continue, so EVERY position of the run is
     compared, not only the prefix up to the first near-tie.
 
@@ -134,7 +134,7 @@ def reference_self_consistency(ref_model, ref_ids: Sequence[int], n_prompt: int)
     want = torch.tensor(ref_ids[n_prompt:], device=logits.device)
     top2 = torch.topk(logits, 2, dim=-1).values
     top = top2[:, 0]
-    ulp = torch.pow(2.0, torch.floor(torch.log2(top.abs().clamp_min(1e-30))) - 7)
+    ulp = torch.pow(2.0, torch.floor(torch.log2(top.abs().clamp_min(1e-30))) - _mant_bits(ref_model))
     chosen = logits.gather(1, want[:, None])[:, 0]
     below = (top - chosen) / ulp
     margin = (top2[:, 0] - top2[:, 1]) / ulp
@@ -145,12 +145,18 @@ def reference_self_consistency(ref_model, ref_ids: Sequence[int], n_prompt: int)
             "how": "reference lookahead ids vs the reference model's own teacher-forced causal forward (argmax per position)"}
 
 
-def _bf16_ulp(x: float) -> float:
+def _mant_bits(model) -> int:
+    """Explicit mantissa bits of the model dtype: the unit in which a logit 'tie' is measured (bf16 7, fp16 10)."""
+    return {torch.bfloat16: 7, torch.float16: 10}.get(next(model.parameters()).dtype, 23)
+
+
+def _bf16_ulp(x: float, mant_bits: int = 7) -> float:
+    """ulp of the model dtype at |x| (bf16 by default; the name is kept for the callers of round 2's first version)."""
     import math
     ax = abs(float(x))
     if ax == 0.0:
         return 2.0 ** -133
-    return 2.0 ** (math.floor(math.log2(ax)) - 7)
+    return 2.0 ** (math.floor(math.log2(ax)) - mant_bits)
 
 
 def compare_ids(our_generate: Callable[[List[int], int], List[int]], ref_ids: Sequence[int], n_prompt: int,
@@ -176,7 +182,7 @@ def compare_ids(our_generate: Callable[[List[int], int], List[int]], ref_ids: Se
             break
         logits = reference_next_logits(ref_model, ref_ids[:i])
         top = logits.max().item()
-        ulp = _bf16_ulp(top)
+        ulp = _bf16_ulp(top, _mant_bits(ref_model))
         la, lb = logits[ours[i]].item(), logits[ref_ids[i]].item()
         srt = torch.topk(logits, 2).values
         divergences.append({"index": i - n_prompt, "ours": int(ours[i]), "ref": int(ref_ids[i]),

@@ -205,6 +205,29 @@ int lade_swiglu(void* stream, const void* gate_up, void* out, int32_t rows, int3
  * HBM idle; the projection then finds (part of) its weights in the 126 MB L2.  ptr 16-byte aligned. */
 int lade_l2_prefetch(void* stream, const void* ptr, int64_t bytes, int32_t n_ctas, int32_t chunk_bytes);
 
+/* fp16 models (the dtype of the reference's README.md:159 / minimal.py:19; the BASELINE configs are bf16): the same
+ * kernels instantiated on the element type -- every rounding point of the bf16 entry point of the same name without the
+ * suffix happens in fp16 instead.  Arguments, layouts and error codes are those of the unsuffixed function.
+ * lade_attn_fwd_f16 picks its kernel like lade_attn_fwd (tcgen05/TMA for head_dim 128, mma.sync for 64 or impl 1). */
+int lade_rmsnorm_f16(void* stream, const void* x, const void* delta, const void* weight, void* h_out, void* out,
+                     int32_t rows, int32_t hidden, float eps);
+int lade_rmsnorm_gather_f16(void* stream, const void* x, const void* delta, const void* weight,
+                            const int32_t* rows_idx, void* out, int32_t n_rows, int32_t hidden, float eps);
+int lade_rope_append_f16(void* stream, const void* qkv, const void* cos_tab, const void* sin_tab,
+                         const int32_t* pos, const int32_t* meta, void* q_out, void* k_cache, void* v_cache,
+                         int32_t rows, int32_t q_pad, int32_t n_heads, int32_t n_kv_heads, int32_t head_dim,
+                         int32_t kv_capacity, int32_t max_pos);
+int lade_swiglu_f16(void* stream, const void* gate_up, void* out, int32_t rows, int32_t inter);
+int lade_argmax_rows_f16(void* stream, const void* logits, int32_t n_rows, int32_t vocab, int32_t ld,
+                         int32_t* out_idx);
+int lade_attn_fwd_f16(void* stream, const void* q, const void* k_cache, const void* v_cache, void* out,
+                      const uint32_t* rowmask, int32_t mask_words, const int32_t* meta, void* scratch, int32_t q_pad,
+                      int32_t n_heads, int32_t n_kv_heads, int32_t head_dim, int32_t kv_capacity,
+                      int32_t kv_bound, int32_t n_splits, int32_t impl);
+int lade_sample_verify_f16(LadeCtx* ctx, void* stream, const void* logits, int32_t ld, int32_t vocab,
+                           const int32_t* argmax_slots, const int32_t* meta, float temperature, int32_t top_k, float top_p,
+                           uint64_t* rng_state, int32_t* decision_out, float* debug_uniforms);
+
 /* ---- token selection / accept / pool update ---------------------------------------------------- */
 
 /* Row-wise argmax with lowest-index tie-break over bf16 logits [n_rows][vocab]

@@ -73,6 +73,11 @@ _SIGNATURES = {
     "lade_version": (C.c_int, []),
 }
 
+# fp16 twins: same signatures as the bf16 entry points
+for _name in ("lade_rmsnorm", "lade_rmsnorm_gather", "lade_rope_append", "lade_swiglu", "lade_argmax_rows", "lade_attn_fwd",
+              "lade_sample_verify"):
+    _SIGNATURES[_name + "_f16"] = _SIGNATURES[_name]
+
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 _lib = None
 

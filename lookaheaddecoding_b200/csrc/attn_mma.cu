@@ -41,23 +41,27 @@ __device__ __forceinline__ void ldmatrix_x4_trans(unsigned& r0, unsigned& r1, un
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a));
 }
-__device__ __forceinline__ void mma_bf16(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+template <typename T>
+__device__ __forceinline__ void mma_16816(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1);
+template <>
+__device__ __forceinline__ void mma_16816<__nv_bfloat16>(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ unsigned pack_bf16(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<unsigned*>(&v);
+template <>
+__device__ __forceinline__ void mma_16816<__half>(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 // swizzled element offset inside a [BN][ATT_D] bf16 tile: 16-byte chunk index XOR (row & 7)
 template <int ATT_D>
 __device__ __forceinline__ int swz(int row, int chunk) { return row * ATT_D + ((chunk ^ (row & 7)) << 3); }
 
-template <int ATT_D>
-__device__ __forceinline__ void load_tile_async(__nv_bfloat16* sK, __nv_bfloat16* sV, const __nv_bfloat16* gK,
-                                                const __nv_bfloat16* gV, int row0, int T, int kv_capacity) {
+template <int ATT_D, typename T>
+__device__ __forceinline__ void load_tile_async(T* sK, T* sV, const T* gK, const T* gV, int row0, int T_rows, int kv_capacity) {
   // 64 rows x (ATT_D / 8) 16-byte chunks per tensor; 256 threads -> 4 (D = 128) or 2 (D = 64) chunks each per tensor
   constexpr int CPR = ATT_D / 8;
 #pragma unroll
@@ -65,24 +69,24 @@ __device__ __forceinline__ void load_tile_async(__nv_bfloat16* sK, __nv_bfloat16
     const int c = threadIdx.x + i * ATT_THREADS;
     const int row = c / CPR, chunk = c % CPR;
     const int grow = row0 + row;
-    const int ok = (grow < T) ? 16 : 0;
+    const int ok = (grow < T_rows) ? 16 : 0;
     const int crow = grow < kv_capacity ? grow : kv_capacity - 1;
     cp_async16(sK + swz<ATT_D>(row, chunk), gK + (long long)crow * ATT_D + chunk * 8, ok);
     cp_async16(sV + swz<ATT_D>(row, chunk), gV + (long long)crow * ATT_D + chunk * 8, ok);
   }
 }
 
-template <int ATT_D>
+template <int ATT_D, typename ET>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
-attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k_cache,
-                    const __nv_bfloat16* __restrict__ v_cache, __nv_bfloat16* __restrict__ out,
+attn_fwd_mma_kernel(const ET* __restrict__ q, const ET* __restrict__ k_cache,
+                    const ET* __restrict__ v_cache, ET* __restrict__ out,
                     const uint32_t* __restrict__ rowmask, int mask_words, const int* __restrict__ meta,
                     float* __restrict__ part_o,
                     float* __restrict__ part_ml, int* __restrict__ counters, int q_pad, int n_heads,
                     int n_kv_heads, int kv_capacity, int n_splits, float inv_sqrt_d) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_raw);
-  __nv_bfloat16* sV = sK + ATT_STAGES * ATT_BN * ATT_D;
+  ET* sK = reinterpret_cast<ET*>(smem_raw);
+  ET* sV = sK + ATT_STAGES * ATT_BN * ATT_D;
   __shared__ int s_last;
 
   const int split = blockIdx.x, h = blockIdx.y, mt = blockIdx.z;
@@ -106,14 +110,14 @@ attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
   const int my_tiles = tile_hi - tile_lo;
 
   const int hk = h / (n_heads / n_kv_heads);
-  const __nv_bfloat16* gK = k_cache + (long long)hk * kv_capacity * ATT_D;
-  const __nv_bfloat16* gV = v_cache + (long long)hk * kv_capacity * ATT_D;
+  const ET* gK = k_cache + (long long)hk * kv_capacity * ATT_D;
+  const ET* gV = v_cache + (long long)hk * kv_capacity * ATT_D;
 
   // prologue: prefetch up to STAGES-1 tiles
 #pragma unroll
   for (int s = 0; s < ATT_STAGES - 1; ++s) {
     if (s < my_tiles)
-      load_tile_async<ATT_D>(sK + s * ATT_BN * ATT_D, sV + s * ATT_BN * ATT_D, gK, gV, (tile_lo + s) * ATT_BN, T, kv_capacity);
+      load_tile_async<ATT_D, ET>(sK + s * ATT_BN * ATT_D, sV + s * ATT_BN * ATT_D, gK, gV, (tile_lo + s) * ATT_BN, T, kv_capacity);
     cp_async_commit();
   }
 
@@ -124,7 +128,7 @@ attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
   constexpr int ND = ATT_D / 8;        // 8-wide n-tiles of the output
   unsigned qf[KK][4];
   {
-    const __nv_bfloat16* qh = q + (long long)h * q_pad * ATT_D;
+    const ET* qh = q + (long long)h * q_pad * ATT_D;
 #pragma unroll
     for (int kk = 0; kk < KK; ++kk) {
       const int col = kk * 16 + (lane & 3) * 2;
@@ -150,15 +154,15 @@ attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
       const int nt = it + ATT_STAGES - 1;
       if (nt < my_tiles) {
         const int st = nt % ATT_STAGES;
-        load_tile_async<ATT_D>(sK + st * ATT_BN * ATT_D, sV + st * ATT_BN * ATT_D, gK, gV, (tile_lo + nt) * ATT_BN, T, kv_capacity);
+        load_tile_async<ATT_D, ET>(sK + st * ATT_BN * ATT_D, sV + st * ATT_BN * ATT_D, gK, gV, (tile_lo + nt) * ATT_BN, T, kv_capacity);
       }
       cp_async_commit();
     }
     cp_async_wait<ATT_STAGES - 1>();
     __syncthreads();
     const int st = it % ATT_STAGES;
-    const __nv_bfloat16* tK = sK + st * ATT_BN * ATT_D;
-    const __nv_bfloat16* tV = sV + st * ATT_BN * ATT_D;
+    const ET* tK = sK + st * ATT_BN * ATT_D;
+    const ET* tV = sV + st * ATT_BN * ATT_D;
     const int col0 = (tile_lo + it) * ATT_BN;
 
     // ---- S = Q K^T
@@ -174,8 +178,8 @@ attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
         const int row = np * 16 + (m >> 1) * 8 + r;
         const int chunk = kk * 2 + (m & 1);
         ldmatrix_x4(b0, b1, b2, b3, tK + swz<ATT_D>(row, chunk));
-        mma_bf16(s_acc[np * 2], qf[kk], b0, b1);
-        mma_bf16(s_acc[np * 2 + 1], qf[kk], b2, b3);
+        mma_16816<ET>(s_acc[np * 2], qf[kk], b0, b1);
+        mma_16816<ET>(s_acc[np * 2 + 1], qf[kk], b2, b3);
       }
     }
 
@@ -195,7 +199,7 @@ attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        float s = bf16_round(bf16_round(s_acc[nt][e]) * inv_sqrt_d);
+        float s = round_to<ET>(round_to<ET>(s_acc[nt][e]) * inv_sqrt_d);
         const unsigned long long vv = (e < 2) ? va : vb;
         if (!((vv >> (nt * 8 + (e & 1))) & 1ull)) s = -INFINITY;
         s_acc[nt][e] = s;
@@ -223,8 +227,8 @@ attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
       ps_a += p0 + p1;
       ps_b += p2 + p3;
       const int ks = nt >> 1;
-      if ((nt & 1) == 0) { pf[ks][0] = pack_bf16(p0, p1); pf[ks][1] = pack_bf16(p2, p3); }
-      else               { pf[ks][2] = pack_bf16(p0, p1); pf[ks][3] = pack_bf16(p2, p3); }
+      if ((nt & 1) == 0) { pf[ks][0] = Elem<ET>::pack2(p0, p1); pf[ks][1] = Elem<ET>::pack2(p2, p3); }
+      else               { pf[ks][2] = Elem<ET>::pack2(p0, p1); pf[ks][3] = Elem<ET>::pack2(p2, p3); }
     }
     l_a = l_a * sc_a + ps_a;
     l_b = l_b * sc_b + ps_b;
@@ -243,8 +247,8 @@ attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
         const int row = ks * 16 + (m & 1) * 8 + r;
         const int chunk = nd * 2 + (m >> 1);
         ldmatrix_x4_trans(b0, b1, b2, b3, tV + swz<ATT_D>(row, chunk));
-        mma_bf16(o_acc[nd * 2], pf[ks], b0, b1);
-        mma_bf16(o_acc[nd * 2 + 1], pf[ks], b2, b3);
+        mma_16816<ET>(o_acc[nd * 2], pf[ks], b0, b1);
+        mma_16816<ET>(o_acc[nd * 2 + 1], pf[ks], b2, b3);
       }
     }
     __syncthreads();  // stage may be overwritten by the next prefetch
@@ -265,9 +269,9 @@ attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
     for (int nt = 0; nt < ND; ++nt) {
       const int col = nt * 8 + (lane & 3) * 2;
       if (row_a < q_pad)
-        *reinterpret_cast<unsigned*>(out + (long long)row_a * HD + h * ATT_D + col) = pack_bf16(o_acc[nt][0] * inv_a, o_acc[nt][1] * inv_a);
+        *reinterpret_cast<unsigned*>(out + (long long)row_a * HD + h * ATT_D + col) = Elem<ET>::pack2(o_acc[nt][0] * inv_a, o_acc[nt][1] * inv_a);
       if (row_b < q_pad)
-        *reinterpret_cast<unsigned*>(out + (long long)row_b * HD + h * ATT_D + col) = pack_bf16(o_acc[nt][2] * inv_b, o_acc[nt][3] * inv_b);
+        *reinterpret_cast<unsigned*>(out + (long long)row_b * HD + h * ATT_D + col) = Elem<ET>::pack2(o_acc[nt][2] * inv_b, o_acc[nt][3] * inv_b);
     }
     return;
   }
@@ -318,24 +322,24 @@ attn_fwd_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
     }
     const float inv = lsum > 0.f ? 1.f / lsum : 0.f;
     uint2 pk;
-    pk.x = pack_bf16(acc.x * inv, acc.y * inv);
-    pk.y = pack_bf16(acc.z * inv, acc.w * inv);
+    pk.x = Elem<ET>::pack2(acc.x * inv, acc.y * inv);
+    pk.y = Elem<ET>::pack2(acc.z * inv, acc.w * inv);
     *reinterpret_cast<uint2*>(out + (long long)row * HD + h * ATT_D + c4 * 4) = pk;
   }
   if (threadIdx.x == 0) counters[h * q_tiles + mt] = 0;
 }
 
-template <int ATT_D>
+template <int ATT_D, typename ET>
 static int attn_fwd_mma_launch_d(cudaStream_t stream, const void* q, const void* k_cache, const void* v_cache, void* out,
                                  const uint32_t* rowmask, int mask_words, const int32_t* meta, void* scratch, int q_pad,
                                  int n_heads, int n_kv_heads, int kv_capacity, int n_splits) {
   const int q_tiles = (q_pad + ATT_BM - 1) / ATT_BM;
-  const size_t smem = (size_t)2 * ATT_STAGES * ATT_BN * ATT_D * sizeof(__nv_bfloat16);
+  const size_t smem = (size_t)2 * ATT_STAGES * ATT_BN * ATT_D * sizeof(ET);
   static unsigned long long attr_devs = 0;   // the attribute is per device (context): one bit per ordinal
   int cur_dev = 0;
   LADE_CUDA_CHECK(cudaGetDevice(&cur_dev));
   if (!((attr_devs >> (cur_dev & 63)) & 1ull)) {
-    LADE_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_mma_kernel<ATT_D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LADE_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_mma_kernel<ATT_D, ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_devs |= 1ull << (cur_dev & 63);
   }
   const long long rows_pad = (long long)q_tiles * ATT_BM;
@@ -345,8 +349,8 @@ static int attn_fwd_mma_launch_d(cudaStream_t stream, const void* q, const void*
   float* part_ml = reinterpret_cast<float*>(counters + ATTN_MAX_COUNTERS);
   float* part_o = part_ml + (long long)n_splits * n_heads * rows_pad * 2;
   dim3 grid(n_splits, n_heads, q_tiles);
-  attn_fwd_mma_kernel<ATT_D><<<grid, ATT_THREADS, smem, stream>>>(
-      (const __nv_bfloat16*)q, (const __nv_bfloat16*)k_cache, (const __nv_bfloat16*)v_cache, (__nv_bfloat16*)out,
+  attn_fwd_mma_kernel<ATT_D, ET><<<grid, ATT_THREADS, smem, stream>>>(
+      (const ET*)q, (const ET*)k_cache, (const ET*)v_cache, (ET*)out,
       rowmask, mask_words, meta, part_o, part_ml, counters, q_pad, n_heads, n_kv_heads, kv_capacity, n_splits,
       1.0f / sqrtf((float)ATT_D));
   LADE_LAUNCH_CHECK("attn_fwd_mma_kernel");
@@ -355,13 +359,13 @@ static int attn_fwd_mma_launch_d(cudaStream_t stream, const void* q, const void*
 
 int attn_fwd_mma_launch(cudaStream_t stream, const void* q, const void* k_cache, const void* v_cache, void* out,
                         const uint32_t* rowmask, int mask_words, const int32_t* meta, void* scratch, int q_pad, int n_heads,
-                        int n_kv_heads, int head_dim, int kv_capacity, int n_splits) {
-  if (head_dim == 128)
-    return attn_fwd_mma_launch_d<128>(stream, q, k_cache, v_cache, out, rowmask, mask_words, meta, scratch, q_pad, n_heads,
-                                      n_kv_heads, kv_capacity, n_splits);
-  if (head_dim == 64)
-    return attn_fwd_mma_launch_d<64>(stream, q, k_cache, v_cache, out, rowmask, mask_words, meta, scratch, q_pad, n_heads,
-                                     n_kv_heads, kv_capacity, n_splits);
+                        int n_kv_heads, int head_dim, int kv_capacity, int n_splits, int is_f16) {
+#define LADE_MMA_DISPATCH(DD, TT)                                                                                        \
+  return attn_fwd_mma_launch_d<DD, TT>(stream, q, k_cache, v_cache, out, rowmask, mask_words, meta, scratch, q_pad, n_heads, \
+                                       n_kv_heads, kv_capacity, n_splits)
+  if (head_dim == 128) { if (is_f16) LADE_MMA_DISPATCH(128, __half); else LADE_MMA_DISPATCH(128, __nv_bfloat16); }
+  if (head_dim == 64) { if (is_f16) LADE_MMA_DISPATCH(64, __half); else LADE_MMA_DISPATCH(64, __nv_bfloat16); }
+#undef LADE_MMA_DISPATCH
   return LADE_EUNSUPPORTED;
 }
 

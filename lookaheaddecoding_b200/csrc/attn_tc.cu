@@ -16,6 +16,7 @@
 
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
 #include <unordered_map>
 
 namespace lade {
@@ -37,7 +38,10 @@ constexpr int TC_SO_STRIDE = 132;                       // floats per staged O r
 constexpr int TC_SO_OFFSET = TC_TILE_BYTES;
 constexpr int TC_SML_OFFSET = 0;
 
-__host__ __device__ constexpr uint32_t umma_idesc(bool b_mn_major) { return umma_idesc_n(128u, b_mn_major); }
+template <typename ET>
+__host__ __device__ constexpr uint32_t umma_idesc(bool b_mn_major) {
+  return umma_idesc_n(128u, b_mn_major, sizeof(ET) == 2 && !std::is_same<ET, __nv_bfloat16>::value);
+}
 
 // Optional per-CTA phase timestamps (clock64) for profiling the kernel's own timeline: 16 slots per CTA
 // (0-7 CTA phases, 8-15 the softmax phases of tile 1 as seen by thread 64).
@@ -49,9 +53,10 @@ enum { TS_START = 0, TS_KFULL0 = 1, TS_SFULL0 = 2, TS_OFINAL = 3, TS_STAGED = 4,
 // ---- kernel ---------------------------------------------------------------------------------------------
 // grid (n_splits, heads, q tiles); when n_splits > 1 the n_splits CTAs of one (head, q tile) form a thread-block
 // cluster and merge their split-KV partials through distributed shared memory.
+template <typename ET>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                   const __grid_constant__ CUtensorMap tmV, __nv_bfloat16* __restrict__ out,
+                   const __grid_constant__ CUtensorMap tmV, ET* __restrict__ out,
                    const uint32_t* __restrict__ rowmask, int mask_words, const int* __restrict__ meta, int q_pad,
                    int n_heads, int n_kv_heads, int n_splits, float inv_sqrt_d, float* __restrict__ part_o,
                    float2* __restrict__ part_ml, int merge_mode) {
@@ -90,7 +95,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int B_QFULL = 0, B_KFULL = 1, B_VFULL = 1 + TC_STAGES, B_FREE = 1 + 2 * TC_STAGES,
             B_SFULL = 1 + 3 * TC_STAGES, B_PFULL = 3 + 3 * TC_STAGES, B_OFINAL = 5 + 3 * TC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
-  __nv_bfloat16* s_xmax = reinterpret_cast<__nv_bfloat16*>(smem + TC_SMEM_TILES + 256);   // [2][4][128] row maxima
+  ET* s_xmax = reinterpret_cast<ET*>(smem + TC_SMEM_TILES + 256);   // [2][4][128] row maxima (model dtype: exact)
   float* s_xsum = reinterpret_cast<float*>(smem + TC_SMEM_TILES + 256);                   // [4][128] row sums (epilogue)
   const uint32_t sQ_a = smem_u32(sQ);
   auto sK_a = [&](int s) { return sQ_a + (uint32_t)TC_TILE_BYTES * (1 + 2 * s); };
@@ -160,8 +165,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   } else if (warp == 1) {
     // ================= MMA issuer (one thread) =================
     if (lane == 0) {
-      constexpr uint32_t IDESC_QK = umma_idesc(false);
-      constexpr uint32_t IDESC_PV = umma_idesc(true);
+      constexpr uint32_t IDESC_QK = umma_idesc<ET>(false);
+      constexpr uint32_t IDESC_PV = umma_idesc<ET>(true);
       auto issue_qk = [&](int j) {
         const int s = j % TC_STAGES;
         mbar_wait(BAR(B_KFULL + s), (j / TC_STAGES) & 1);
@@ -236,13 +241,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int i = 0; i < 32; ++i) mq[i & 3] = fmaxf(mq[i & 3], ((mb >> i) & 1u) ? v[i] : -INFINITY);
       }
       const float mx_raw = fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3]));
-      __nv_bfloat16* xm = s_xmax + (j & 1) * 512;   // slot parity: no write-after-read race across tiles
-      xm[q4 * 128 + row_l] = __float2bfloat16_rn(mx_raw == -INFINITY ? -INFINITY : bf16_round(mx_raw) * inv_sqrt_d);
+      ET* xm = s_xmax + (j & 1) * 512;   // slot parity: no write-after-read race across tiles
+      xm[q4 * 128 + row_l] = Elem<ET>::from_f(mx_raw == -INFINITY ? -INFINITY : round_to<ET>(mx_raw) * inv_sqrt_d);
       if (j == 1) TC_STAMP(11, 64);
       named_bar_sync(1, TC_SOFTMAX_THREADS);
       if (j == 1) TC_STAMP(12, 64);
-      const float mx = fmaxf(fmaxf(__bfloat162float(xm[row_l]), __bfloat162float(xm[128 + row_l])),
-                             fmaxf(__bfloat162float(xm[256 + row_l]), __bfloat162float(xm[384 + row_l])));
+      const float mx = fmaxf(fmaxf(Elem<ET>::to_f(xm[row_l]), Elem<ET>::to_f(xm[128 + row_l])),
+                             fmaxf(Elem<ET>::to_f(xm[256 + row_l]), Elem<ET>::to_f(xm[384 + row_l])));
       // lazy rescale: keep the stale max while it is within 2^8 of the running max (all four threads agree)
       if (j == 0) {
         m_used = mx;
@@ -280,15 +285,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const int i = g * 8 + e;
             // reference rounding points, two elements per cvt: bf16(bf16(s) * (1/sqrt(d))).  The halves are unpacked
             // by hand (one shift, one mask): __bfloat1622float2 costs an extra PRMT per pair.
-            const uint32_t u1 = pack2_bf16(v[i], v[i + 1]);
-            const uint32_t u2 = pack2_bf16(__uint_as_float(u1 << 16) * inv_sqrt_d, __uint_as_float(u1 & 0xffff0000u) * inv_sqrt_d);
-            p[e] = ex2_approx(__uint_as_float(u2 << 16) * TC_LOG2E - off);
-            p[e + 1] = ex2_approx(__uint_as_float(u2 & 0xffff0000u) * TC_LOG2E - off);
+            float r0, r1;
+            round_scale_round2<ET>(v[i], v[i + 1], inv_sqrt_d, r0, r1);
+            p[e] = ex2_approx(r0 * TC_LOG2E - off);
+            p[e + 1] = ex2_approx(r1 * TC_LOG2E - off);
             ps4[g] += p[e] + p[e + 1];
           }
           uint4 pk;
-          pk.x = pack2_bf16(p[0], p[1]); pk.y = pack2_bf16(p[2], p[3]);
-          pk.z = pack2_bf16(p[4], p[5]); pk.w = pack2_bf16(p[6], p[7]);
+          pk.x = Elem<ET>::pack2(p[0], p[1]); pk.y = Elem<ET>::pack2(p[2], p[3]);
+          pk.z = Elem<ET>::pack2(p[4], p[5]); pk.w = Elem<ET>::pack2(p[6], p[7]);
           const int cc = (q4 & 1) * 4 + g;
           *reinterpret_cast<uint4*>(prow + ((cc ^ (row_l & 7)) << 4)) = pk;
         }
@@ -299,15 +304,15 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
           for (int e = 0; e < 8; e += 2) {
             const int i = g * 8 + e;
-            const uint32_t u1 = pack2_bf16(v[i], v[i + 1]);
-            const uint32_t u2 = pack2_bf16(__uint_as_float(u1 << 16) * inv_sqrt_d, __uint_as_float(u1 & 0xffff0000u) * inv_sqrt_d);
-            p[e] = ((mb >> i) & 1u) ? ex2_approx(__uint_as_float(u2 << 16) * TC_LOG2E - off) : 0.f;
-            p[e + 1] = ((mb >> (i + 1)) & 1u) ? ex2_approx(__uint_as_float(u2 & 0xffff0000u) * TC_LOG2E - off) : 0.f;
+            float r0, r1;
+            round_scale_round2<ET>(v[i], v[i + 1], inv_sqrt_d, r0, r1);
+            p[e] = ((mb >> i) & 1u) ? ex2_approx(r0 * TC_LOG2E - off) : 0.f;
+            p[e + 1] = ((mb >> (i + 1)) & 1u) ? ex2_approx(r1 * TC_LOG2E - off) : 0.f;
             ps4[g] += p[e] + p[e + 1];
           }
           uint4 pk;
-          pk.x = pack2_bf16(p[0], p[1]); pk.y = pack2_bf16(p[2], p[3]);
-          pk.z = pack2_bf16(p[4], p[5]); pk.w = pack2_bf16(p[6], p[7]);
+          pk.x = Elem<ET>::pack2(p[0], p[1]); pk.y = Elem<ET>::pack2(p[2], p[3]);
+          pk.z = Elem<ET>::pack2(p[4], p[5]); pk.w = Elem<ET>::pack2(p[6], p[7]);
           const int cc = (q4 & 1) * 4 + g;
           *reinterpret_cast<uint4*>(prow + ((cc ^ (row_l & 7)) << 4)) = pk;
         }
@@ -353,10 +358,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int v4 = 0; v4 < 4; ++v4) {
           uint4 pk;
-          pk.x = pack2_bf16(ov[v4 * 8 + 0] * inv, ov[v4 * 8 + 1] * inv);
-          pk.y = pack2_bf16(ov[v4 * 8 + 2] * inv, ov[v4 * 8 + 3] * inv);
-          pk.z = pack2_bf16(ov[v4 * 8 + 4] * inv, ov[v4 * 8 + 5] * inv);
-          pk.w = pack2_bf16(ov[v4 * 8 + 6] * inv, ov[v4 * 8 + 7] * inv);
+          pk.x = Elem<ET>::pack2(ov[v4 * 8 + 0] * inv, ov[v4 * 8 + 1] * inv);
+          pk.y = Elem<ET>::pack2(ov[v4 * 8 + 2] * inv, ov[v4 * 8 + 3] * inv);
+          pk.z = Elem<ET>::pack2(ov[v4 * 8 + 4] * inv, ov[v4 * 8 + 5] * inv);
+          pk.w = Elem<ET>::pack2(ov[v4 * 8 + 6] * inv, ov[v4 * 8 + 7] * inv);
           dst[v4] = pk;
         }
       }
@@ -440,10 +445,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int v4 = 0; v4 < 4; ++v4) {
           uint4 pk;
-          pk.x = pack2_bf16(ov[v4 * 8 + 0] * inv, ov[v4 * 8 + 1] * inv);
-          pk.y = pack2_bf16(ov[v4 * 8 + 2] * inv, ov[v4 * 8 + 3] * inv);
-          pk.z = pack2_bf16(ov[v4 * 8 + 4] * inv, ov[v4 * 8 + 5] * inv);
-          pk.w = pack2_bf16(ov[v4 * 8 + 6] * inv, ov[v4 * 8 + 7] * inv);
+          pk.x = Elem<ET>::pack2(ov[v4 * 8 + 0] * inv, ov[v4 * 8 + 1] * inv);
+          pk.y = Elem<ET>::pack2(ov[v4 * 8 + 2] * inv, ov[v4 * 8 + 3] * inv);
+          pk.z = Elem<ET>::pack2(ov[v4 * 8 + 4] * inv, ov[v4 * 8 + 5] * inv);
+          pk.w = Elem<ET>::pack2(ov[v4 * 8 + 6] * inv, ov[v4 * 8 + 7] * inv);
           dst[v4] = pk;
         }
       }
@@ -503,10 +508,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
       for (int v4 = 0; v4 < 4; ++v4) {
         uint4 pk;
-        pk.x = pack2_bf16(ov[v4 * 8 + 0] * inv, ov[v4 * 8 + 1] * inv);
-        pk.y = pack2_bf16(ov[v4 * 8 + 2] * inv, ov[v4 * 8 + 3] * inv);
-        pk.z = pack2_bf16(ov[v4 * 8 + 4] * inv, ov[v4 * 8 + 5] * inv);
-        pk.w = pack2_bf16(ov[v4 * 8 + 6] * inv, ov[v4 * 8 + 7] * inv);
+        pk.x = Elem<ET>::pack2(ov[v4 * 8 + 0] * inv, ov[v4 * 8 + 1] * inv);
+        pk.y = Elem<ET>::pack2(ov[v4 * 8 + 2] * inv, ov[v4 * 8 + 3] * inv);
+        pk.z = Elem<ET>::pack2(ov[v4 * 8 + 4] * inv, ov[v4 * 8 + 5] * inv);
+        pk.w = Elem<ET>::pack2(ov[v4 * 8 + 6] * inv, ov[v4 * 8 + 7] * inv);
         dst[v4] = pk;
       }
     }
@@ -593,9 +598,10 @@ static bool pdl_enabled() {
   return v != 0;
 }
 
-int attn_fwd_tc_launch(cudaStream_t stream, const void* q, const void* k_cache, const void* v_cache, void* out,
-                       const uint32_t* rowmask, int mask_words, const int32_t* meta, void* scratch, int q_pad, int n_heads,
-                       int n_kv_heads, int head_dim, int kv_capacity, int kv_bound, int n_splits) {
+template <typename ET>
+static int attn_fwd_tc_launch_t(cudaStream_t stream, const void* q, const void* k_cache, const void* v_cache, void* out,
+                                const uint32_t* rowmask, int mask_words, const int32_t* meta, void* scratch, int q_pad,
+                                int n_heads, int n_kv_heads, int head_dim, int kv_capacity, int kv_bound, int n_splits) {
   (void)kv_bound;
   if (head_dim != TC_D) return LADE_EUNSUPPORTED;
   const int q_tiles = (q_pad + TC_BM - 1) / TC_BM;
@@ -612,7 +618,7 @@ int attn_fwd_tc_launch(cudaStream_t stream, const void* q, const void* k_cache, 
   int cur_dev = 0;
   LADE_CUDA_CHECK(cudaGetDevice(&cur_dev));
   if (!((attr_devs >> (cur_dev & 63)) & 1ull)) {
-    LADE_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    LADE_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel<ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     attr_devs |= 1ull << (cur_dev & 63);
   }
   cudaLaunchConfig_t cfg = {};
@@ -635,10 +641,20 @@ int attn_fwd_tc_launch(cudaStream_t stream, const void* q, const void* k_cache, 
   // scratch (lade_attn_scratch_bytes): [64 KB reserved][partial O: n_splits * n_heads * rows_pad * D fp32][(m, l) per row]
   float* part_o = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 65536);
   float2* part_ml = reinterpret_cast<float2*>(part_o + (size_t)n_splits * n_heads * q_tiles * TC_BM * TC_D);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_fwd_tc_kernel, tmQ, tmK, tmV, (__nv_bfloat16*)out, rowmask, mask_words, meta,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_fwd_tc_kernel<ET>, tmQ, tmK, tmV, (ET*)out, rowmask, mask_words, meta,
                                      q_pad, n_heads, n_kv_heads, n_splits, inv_sqrt_d, part_o, part_ml, merge_mode());
   if (e != cudaSuccess) { set_cuda_error(e, "cudaLaunchKernelEx(attn_fwd_tc_kernel)"); return LADE_ECUDA; }
   return LADE_OK;
+}
+
+int attn_fwd_tc_launch(cudaStream_t stream, const void* q, const void* k_cache, const void* v_cache, void* out,
+                       const uint32_t* rowmask, int mask_words, const int32_t* meta, void* scratch, int q_pad, int n_heads,
+                       int n_kv_heads, int head_dim, int kv_capacity, int kv_bound, int n_splits, int is_f16) {
+  if (is_f16)
+    return attn_fwd_tc_launch_t<__half>(stream, q, k_cache, v_cache, out, rowmask, mask_words, meta, scratch, q_pad, n_heads,
+                                        n_kv_heads, head_dim, kv_capacity, kv_bound, n_splits);
+  return attn_fwd_tc_launch_t<__nv_bfloat16>(stream, q, k_cache, v_cache, out, rowmask, mask_words, meta, scratch, q_pad,
+                                             n_heads, n_kv_heads, head_dim, kv_capacity, kv_bound, n_splits);
 }
 
 }  // namespace lade

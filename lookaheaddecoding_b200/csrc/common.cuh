@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include "../../include/lade_sm100.h"
 
@@ -87,5 +88,28 @@ __device__ __forceinline__ uint32_t visible_bits32(const uint32_t* __restrict__ 
 }
 
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// Element type of a model (bf16 or fp16): conversions with the rounding the reference's tensors get (round to nearest
+// even into the model dtype after every op, lade/models/modeling_llama.py runs in `torch_dtype`).
+template <typename T> struct Elem;
+template <> struct Elem<__nv_bfloat16> {
+  static __device__ __forceinline__ float to_f(__nv_bfloat16 x) { return __bfloat162float(x); }
+  static __device__ __forceinline__ __nv_bfloat16 from_f(float x) { return __float2bfloat16_rn(x); }
+  static __device__ __forceinline__ unsigned pack2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<unsigned*>(&v);
+  }
+  static __device__ __forceinline__ unsigned key16(__nv_bfloat16 x) { return __bfloat16_as_ushort(x); }
+};
+template <> struct Elem<__half> {
+  static __device__ __forceinline__ float to_f(__half x) { return __half2float(x); }
+  static __device__ __forceinline__ __half from_f(float x) { return __float2half_rn(x); }
+  static __device__ __forceinline__ unsigned pack2(float lo, float hi) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<unsigned*>(&v);
+  }
+  static __device__ __forceinline__ unsigned key16(__half x) { return __half_as_ushort(x); }
+};
+template <typename T> __device__ __forceinline__ float round_to(float x) { return Elem<T>::to_f(Elem<T>::from_f(x)); }
 
 }  // namespace lade

@@ -55,21 +55,25 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* s_red) {
 }
 
 // scores = logits / T in fp32 (TemperatureLogitsWarper), softmax in fp32
-__device__ __forceinline__ float score_of(const __nv_bfloat16* row, int t, float temperature) {
-  return __bfloat162float(row[t]) / temperature;
+template <typename T>
+__device__ __forceinline__ float score_of(const T* row, int t, float temperature) {
+  return Elem<T>::to_f(row[t]) / temperature;
 }
 
-// bf16 bit pattern -> 16-bit key that orders like the value (the logits are bf16: at most 65536 distinct scores, so
-// top-k / top-p cut-offs are exact thresholds on this key, found with two 256-bin histograms instead of a sort)
-__device__ __forceinline__ unsigned key_of(__nv_bfloat16 x) {
-  const unsigned b = __bfloat16_as_ushort(x);
+// 16-bit float bit pattern (bf16 or fp16: sign-magnitude) -> 16-bit key that orders like the value (the logits have a
+// 16-bit dtype: at most 65536 distinct scores, so top-k / top-p cut-offs are exact thresholds on this key, found with
+// two 256-bin histograms instead of a sort)
+template <typename T>
+__device__ __forceinline__ unsigned key_of(T x) {
+  const unsigned b = Elem<T>::key16(x);
   return (b & 0x8000u) ? (~b & 0xffffu) : (b | 0x8000u);
 }
 
 // The warped distribution of one logits row: p[t] = (key(t) >= thr) * exp(score_t - mx) / sum.
 struct RowDist { float mx, sum; unsigned thr; };
 
-__device__ __forceinline__ float e_of(const __nv_bfloat16* row, int t, float temperature, const RowDist& d) {
+template <typename T>
+__device__ __forceinline__ float e_of(const T* row, int t, float temperature, const RowDist& d) {
   return key_of(row[t]) >= d.thr ? __expf(score_of(row, t, temperature) - d.mx) : 0.f;
 }
 
@@ -77,7 +81,8 @@ __device__ __forceinline__ float e_of(const __nv_bfloat16* row, int t, float tem
 // TopPLogitsWarper (ascending cumulative probability of the top-k-filtered softmax: drop while cum <= 1 - top_p;
 // min_tokens_to_keep = 1).  Scores tie in whole buckets of equal bf16 value; a bucket is dropped only when all of it
 // can go (torch.sort breaks such ties arbitrarily, so there is no reference order to follow inside a bucket).
-__device__ RowDist row_dist(const __nv_bfloat16* row, int vocab, float temperature, int top_k, float top_p, float* s_red,
+template <typename T>
+__device__ RowDist row_dist(const T* row, int vocab, float temperature, int top_k, float top_p, float* s_red,
                             int* s_cnt, float* s_mass, int* s_sel) {
   RowDist d;
   float mx = -INFINITY;
@@ -158,7 +163,8 @@ __device__ RowDist row_dist(const __nv_bfloat16* row, int vocab, float temperatu
 
 // One draw from the distribution e_t = exp(score_t - mx) over t not in zset[0..n_z), by inverse CDF:
 // the smallest t whose running mass reaches u * total.  Each thread owns one contiguous chunk of the vocabulary.
-__device__ int multinomial_excluding(const __nv_bfloat16* row, int vocab, float temperature, const RowDist& rd, float u,
+template <typename T>
+__device__ int multinomial_excluding(const T* row, int vocab, float temperature, const RowDist& rd, float u,
                                      const int* zset, int n_z, float* s_scan, int* s_pick) {
   const int chunk = (vocab + blockDim.x - 1) / blockDim.x;
   const int lo = threadIdx.x * chunk, hi = min(vocab, lo + chunk);
@@ -219,8 +225,9 @@ __device__ int multinomial_excluding(const __nv_bfloat16* row, int vocab, float 
 // decision_out: the record lade_commit_decision consumes --
 //   [first hit, max_hit, n_new, hits[GS], new_tok[WCAP] | max_hit_idx, flags (1 sampling, 2 filtered row present),
 //    finished-by-extra-eos, 0, filtered[W]]
+template <typename T>
 __global__ void __launch_bounds__(SMP_THREADS, 1)
-sample_verify_kernel(int* st, Dims d, const __nv_bfloat16* __restrict__ logits, int ld, int vocab,
+sample_verify_kernel(int* st, Dims d, const T* __restrict__ logits, int ld, int vocab,
                      const int* __restrict__ am, const int* __restrict__ meta, float temperature, int top_k, float top_p,
                      unsigned long long* rng_state, int* __restrict__ rec, float* dbg) {
   __shared__ float s_red[32];
@@ -258,7 +265,7 @@ sample_verify_kernel(int* st, Dims d, const __nv_bfloat16* __restrict__ logits, 
     return u;
   };
 
-  const __nv_bfloat16* row0 = logits;           // slot 0 = the next-token row (lade_step_layout's lm_rows)
+  const T* row0 = logits;                       // slot 0 = the next-token row (lade_step_layout's lm_rows)
   if (phase != 2 || n_ng == 0) {                // :458-480, :543-546
     const RowDist rs = row_dist(row0, vocab, temperature, top_k, top_p, s_red, s_cnt, s_mass, s_sel);
     if (t == 0) s_u = draw();
@@ -271,7 +278,7 @@ sample_verify_kernel(int* st, Dims d, const __nv_bfloat16* __restrict__ logits, 
     __syncthreads();
     for (int i = 0; i < GS; ++i) {
       const int cur = s_ctl[1];
-      const __nv_bfloat16* row = logits + (long long)cur * ld;
+      const T* row = logits + (long long)cur * ld;
       const RowDist rs = row_dist(row, vocab, temperature, top_k, top_p, s_red, s_cnt, s_mass, s_sel);
       if (t == 0) {
         int n_z = 0;
@@ -360,20 +367,35 @@ sample_verify_kernel(int* st, Dims d, const __nv_bfloat16* __restrict__ logits, 
 
 using namespace lade;
 
+template <typename T>
+static int sample_verify_impl(LadeCtx* ctx, void* stream, const void* logits, int32_t ld, int32_t vocab,
+                              const int32_t* argmax_slots, const int32_t* meta, float temperature, int32_t top_k, float top_p,
+                              uint64_t* rng_state, int32_t* decision_out, float* debug_uniforms) {
+  if (!ctx || !logits || !argmax_slots || !meta || !rng_state || !decision_out) return LADE_EINVAL;
+  if (!(temperature > 0.f) || vocab < 1 || ld < vocab || top_k < 0 || !(top_p > 0.f) || top_p > 1.f) return LADE_EINVAL;
+  if (ctx->d.D != 1) return LADE_ESTATE;                                   // no LP on the sampling path
+  if (ctx->d.G > SMP_MAX_NGRAMS || ctx->d.GS > 64) return LADE_EUNSUPPORTED;
+  sample_verify_kernel<T><<<1, SMP_THREADS, 0, (cudaStream_t)stream>>>(
+      ctx->state, ctx->d, (const T*)logits, ld, vocab, argmax_slots, meta, temperature, top_k, top_p,
+      reinterpret_cast<unsigned long long*>(rng_state), decision_out, debug_uniforms);
+  LADE_LAUNCH_CHECK("sample_verify_kernel");
+  return LADE_OK;
+}
+
 extern "C" {
 
 int lade_sample_verify(LadeCtx* ctx, void* stream, const void* logits, int32_t ld, int32_t vocab,
                        const int32_t* argmax_slots, const int32_t* meta, float temperature, int32_t top_k, float top_p,
                        uint64_t* rng_state, int32_t* decision_out, float* debug_uniforms) {
-  if (!ctx || !logits || !argmax_slots || !meta || !rng_state || !decision_out) return LADE_EINVAL;
-  if (!(temperature > 0.f) || vocab < 1 || ld < vocab || top_k < 0 || !(top_p > 0.f) || top_p > 1.f) return LADE_EINVAL;
-  if (ctx->d.D != 1) return LADE_ESTATE;                                   // no LP on the sampling path
-  if (ctx->d.G > SMP_MAX_NGRAMS || ctx->d.GS > 64) return LADE_EUNSUPPORTED;
-  sample_verify_kernel<<<1, SMP_THREADS, 0, (cudaStream_t)stream>>>(
-      ctx->state, ctx->d, (const __nv_bfloat16*)logits, ld, vocab, argmax_slots, meta, temperature, top_k, top_p,
-      reinterpret_cast<unsigned long long*>(rng_state), decision_out, debug_uniforms);
-  LADE_LAUNCH_CHECK("sample_verify_kernel");
-  return LADE_OK;
+  return sample_verify_impl<__nv_bfloat16>(ctx, stream, logits, ld, vocab, argmax_slots, meta, temperature, top_k, top_p,
+                                           rng_state, decision_out, debug_uniforms);
+}
+
+int lade_sample_verify_f16(LadeCtx* ctx, void* stream, const void* logits, int32_t ld, int32_t vocab,
+                           const int32_t* argmax_slots, const int32_t* meta, float temperature, int32_t top_k, float top_p,
+                           uint64_t* rng_state, int32_t* decision_out, float* debug_uniforms) {
+  return sample_verify_impl<__half>(ctx, stream, logits, ld, vocab, argmax_slots, meta, temperature, top_k, top_p,
+                                    rng_state, decision_out, debug_uniforms);
 }
 
 }  // extern "C"

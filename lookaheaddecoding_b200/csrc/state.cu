@@ -563,9 +563,10 @@ __global__ void kv_compact_kernel(const int* __restrict__ res, __nv_bfloat16* k_
 }
 
 // ---- row-wise argmax (lowest index on ties) ------------------------------------------------------------
-__global__ void argmax_rows_kernel(const __nv_bfloat16* __restrict__ logits, int vocab, int ld, int* out_idx) {
+template <typename T>
+__global__ void argmax_rows_kernel(const T* __restrict__ logits, int vocab, int ld, int* out_idx) {
   const int row = blockIdx.x;
-  const __nv_bfloat16* p = logits + (long long)row * ld;
+  const T* p = logits + (long long)row * ld;
   float best = -INFINITY;
   int bi = 0x7fffffff;
   const int t = threadIdx.x;
@@ -575,21 +576,21 @@ __global__ void argmax_rows_kernel(const __nv_bfloat16* __restrict__ logits, int
   if (aligned) {
     for (int i = t; i < nvec; i += blockDim.x) {
       const uint4 v = pv[i];
-      const __nv_bfloat16* e = reinterpret_cast<const __nv_bfloat16*>(&v);
+      const T* e = reinterpret_cast<const T*>(&v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float f = __bfloat162float(e[j]);
+        const float f = Elem<T>::to_f(e[j]);
         const int id = i * 8 + j;
         if (f > best || (f == best && id < bi)) { best = f; bi = id; }
       }
     }
     for (int id = nvec * 8 + t; id < vocab; id += blockDim.x) {
-      const float f = __bfloat162float(p[id]);
+      const float f = Elem<T>::to_f(p[id]);
       if (f > best || (f == best && id < bi)) { best = f; bi = id; }
     }
   } else {
     for (int id = t; id < vocab; id += blockDim.x) {
-      const float f = __bfloat162float(p[id]);
+      const float f = Elem<T>::to_f(p[id]);
       if (f > best || (f == best && id < bi)) { best = f; bi = id; }
     }
   }
@@ -757,7 +758,15 @@ int lade_kv_compact(void* stream, const int32_t* result, void* k_base, void* v_b
 int lade_argmax_rows(void* stream, const void* logits, int32_t n_rows, int32_t vocab, int32_t ld,
                      int32_t* out_idx) {
   if (!logits || !out_idx || n_rows < 1 || vocab < 1 || ld < vocab) return LADE_EINVAL;
-  argmax_rows_kernel<<<n_rows, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)logits, vocab, ld, out_idx);
+  argmax_rows_kernel<__nv_bfloat16><<<n_rows, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)logits, vocab, ld, out_idx);
+  LADE_LAUNCH_CHECK("argmax_rows_kernel");
+  return LADE_OK;
+}
+
+int lade_argmax_rows_f16(void* stream, const void* logits, int32_t n_rows, int32_t vocab, int32_t ld,
+                         int32_t* out_idx) {
+  if (!logits || !out_idx || n_rows < 1 || vocab < 1 || ld < vocab) return LADE_EINVAL;
+  argmax_rows_kernel<__half><<<n_rows, 256, 0, (cudaStream_t)stream>>>((const __half*)logits, vocab, ld, out_idx);
   LADE_LAUNCH_CHECK("argmax_rows_kernel");
   return LADE_OK;
 }

@@ -102,8 +102,10 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): f32 accumulate, bf16 x bf16, M=128, N = n (multiple of 16).
-__host__ __device__ constexpr uint32_t umma_idesc_n(uint32_t n, bool b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+__host__ __device__ constexpr uint32_t umma_idesc_n(uint32_t n, bool b_mn_major, bool fp16_operands = false) {
+  // bits [7,10) = A format, [10,13) = B format: 0 = F16, 1 = BF16 (kind::f16)
+  return (1u << 4) | ((fp16_operands ? 0u : 1u) << 7) | ((fp16_operands ? 0u : 1u) << 10) | ((b_mn_major ? 1u : 0u) << 16) |
+         ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -114,6 +116,27 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
+// The reference's two rounding points of a score pair: r = T(T(s) * c), returned as fp32 (T = the model dtype).
+// bf16: the halves of a packed pair are unpacked by hand with one shift and one mask; fp16 needs real conversions.
+template <typename ET>
+__device__ __forceinline__ void round_scale_round2(float a, float b, float c, float& r0, float& r1);
+template <>
+__device__ __forceinline__ void round_scale_round2<__nv_bfloat16>(float a, float b, float c, float& r0, float& r1) {
+  __nv_bfloat162 v1 = __floats2bfloat162_rn(a, b);
+  const uint32_t u1 = *reinterpret_cast<uint32_t*>(&v1);
+  __nv_bfloat162 v2 = __floats2bfloat162_rn(__uint_as_float(u1 << 16) * c, __uint_as_float(u1 & 0xffff0000u) * c);
+  const uint32_t u2 = *reinterpret_cast<uint32_t*>(&v2);
+  r0 = __uint_as_float(u2 << 16);
+  r1 = __uint_as_float(u2 & 0xffff0000u);
+}
+template <>
+__device__ __forceinline__ void round_scale_round2<__half>(float a, float b, float c, float& r0, float& r1) {
+  const float2 f1 = __half22float2(__floats2half2_rn(a, b));
+  const float2 f2 = __half22float2(__floats2half2_rn(f1.x * c, f1.y * c));
+  r0 = f2.x;
+  r1 = f2.y;
+}
+
 __device__ __forceinline__ unsigned pack2_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<unsigned*>(&v);

@@ -75,8 +75,18 @@ class LookaheadEngine:
         p0 = next(model.parameters())
         if p0.device.type != "cuda":
             raise LadeError("LookaheadEngine needs the model on a CUDA device (no CPU fallback)")
-        if p0.dtype != torch.bfloat16:
-            raise LadeError(f"LookaheadEngine supports bf16 models only (got {p0.dtype})")
+        if p0.dtype not in (torch.bfloat16, torch.float16):
+            raise LadeError(f"LookaheadEngine supports bf16 and fp16 models (got {p0.dtype})")
+        # element type of the model: every kernel exists per dtype (bf16: the unsuffixed C-ABI entry points, fp16: *_f16)
+        self.dt = p0.dtype
+        sfx = "" if self.dt == torch.bfloat16 else "_f16"
+        self.k_rmsnorm = getattr(self.lib, "lade_rmsnorm" + sfx)
+        self.k_rmsnorm_gather = getattr(self.lib, "lade_rmsnorm_gather" + sfx)
+        self.k_rope_append = getattr(self.lib, "lade_rope_append" + sfx)
+        self.k_swiglu = getattr(self.lib, "lade_swiglu" + sfx)
+        self.k_argmax_rows = getattr(self.lib, "lade_argmax_rows" + sfx)
+        self.k_attn_fwd = getattr(self.lib, "lade_attn_fwd" + sfx)
+        self.k_sample_verify = getattr(self.lib, "lade_sample_verify" + sfx)
         if level < 3:
             raise LadeError("LEVEL must be >= 3 (lade/decoding.py:902)")
         if guess_set_size == -1:
@@ -197,11 +207,11 @@ class LookaheadEngine:
         t = torch.arange(self.table_len, dtype=inv_freq.dtype)
         freqs = torch.outer(t, inv_freq)
         emb = torch.cat((freqs, freqs), dim=-1)
-        self.cos = emb.cos().to(torch.bfloat16).to(self.dev).contiguous()
-        self.sin = emb.sin().to(torch.bfloat16).to(self.dev).contiguous()
+        self.cos = emb.cos().to(self.dt).to(self.dev).contiguous()
+        self.sin = emb.sin().to(self.dt).to(self.dev).contiguous()
 
     def _alloc(self, rows: int):
-        dev, bf = self.dev, torch.bfloat16
+        dev, bf = self.dev, self.dt
         self.rows_cap = rows
         i32 = dict(dtype=torch.int32, device=dev)
         self.ids = torch.zeros(rows, **i32)
@@ -305,18 +315,18 @@ class LookaheadEngine:
         for l in range(L):
             n += self._prefetch([(self.w_qkv[l], 0)], pf[0])                              # beside rmsnorm
             if "norm" not in skip:
-                check(lib.lade_rmsnorm(stream, _ptr(h), _ptr(delta), _ptr(self.ln1[l]), _ptr(h) if delta is not None else 0,
+                check(self.k_rmsnorm(stream, _ptr(h), _ptr(delta), _ptr(self.ln1[l]), _ptr(h) if delta is not None else 0,
                                        _ptr(xn), rows, self.H, self.eps), "lade_rmsnorm"); n += 1
             if "gemm" not in skip:
                 torch.mm(xn, self.w_qkv[l].t(), out=qkv)
             n += self._prefetch([(self.w_o[l], 0), (self.w_gu[l], 0)], pf[1])              # beside rope + attention
             kc, vc = self.kv[l, 0], self.kv[l, 1]
             if "rope" not in skip:
-                check(lib.lade_rope_append(stream, _ptr(qkv), _ptr(self.cos), _ptr(self.sin), _ptr(self.pos), _ptr(self.meta),
+                check(self.k_rope_append(stream, _ptr(qkv), _ptr(self.cos), _ptr(self.sin), _ptr(self.pos), _ptr(self.meta),
                                            _ptr(qb), _ptr(kc), _ptr(vc), rows, rows, self.nh, self.nkv, self.D,
                                            self.kv_capacity, self.table_len), "lade_rope_append"); n += 1
             if "attn" not in skip:
-                check(lib.lade_attn_fwd(stream, _ptr(qb), _ptr(kc), _ptr(vc), _ptr(attn_out), _ptr(self.rowmask) if mw else 0, mw,
+                check(self.k_attn_fwd(stream, _ptr(qb), _ptr(kc), _ptr(vc), _ptr(attn_out), _ptr(self.rowmask) if mw else 0, mw,
                                         _ptr(self.meta), _ptr(self.attn_scratch), rows, self.nh, self.nkv, self.D,
                                         self.kv_capacity, kv_bound, self.attn_splits, self.attn_impl), "lade_attn_fwd"); n += 1
             if "gemm" not in skip:
@@ -324,27 +334,27 @@ class LookaheadEngine:
             gu_done = max(0, int(pf[1] * 1e6) - self.w_o[l].numel() * 2) & ~15
             n += self._prefetch([(self.w_gu[l], gu_done)], pf[2])                          # beside rmsnorm
             if "norm" not in skip:
-                check(lib.lade_rmsnorm(stream, _ptr(h), _ptr(o_buf), _ptr(self.ln2[l]), _ptr(h), _ptr(xn), rows, self.H,
+                check(self.k_rmsnorm(stream, _ptr(h), _ptr(o_buf), _ptr(self.ln2[l]), _ptr(h), _ptr(xn), rows, self.H,
                                        self.eps), "lade_rmsnorm"); n += 1
             if "gemm" not in skip:
                 torch.mm(xn, self.w_gu[l].t(), out=gu)
             n += self._prefetch([(self.w_down[l], 0)], pf[3])                              # beside swiglu
             if "swiglu" not in skip:
-                check(lib.lade_swiglu(stream, _ptr(gu), _ptr(act), rows, self.I), "lade_swiglu"); n += 1
+                check(self.k_swiglu(stream, _ptr(gu), _ptr(act), rows, self.I), "lade_swiglu"); n += 1
             if "gemm" not in skip:
                 torch.mm(act, self.w_down[l].t(), out=d_buf)
             delta = d_buf
         n += self._prefetch([(self.lm_head, 0)], pf[4])                                    # beside the final norm
-        check(lib.lade_rmsnorm_gather(stream, _ptr(h), _ptr(delta), _ptr(self.norm_w), _ptr(self.lm_rows),
+        check(self.k_rmsnorm_gather(stream, _ptr(h), _ptr(delta), _ptr(self.norm_w), _ptr(self.lm_rows),
                                       _ptr(self.xn_lm), self.lm_cap, self.H, self.eps), "lade_rmsnorm_gather"); n += 1
         self._prefetch_join()
         torch.mm(self.xn_lm, self.lm_head.t(), out=self.logits)
-        check(lib.lade_argmax_rows(stream, _ptr(self.logits), self.lm_cap, self.V, self.V, _ptr(self.am)),
+        check(self.k_argmax_rows(stream, _ptr(self.logits), self.lm_cap, self.V, self.V, _ptr(self.am)),
               "lade_argmax_rows"); n += 1
         if not commit:
             return n
         if commit == "sample":      # verification + residual draw on device (Philox), then the state update
-            check(lib.lade_sample_verify(self._ctx, stream, _ptr(self.logits), self.V, self.V, _ptr(self.am), _ptr(self.meta),
+            check(self.k_sample_verify(self._ctx, stream, _ptr(self.logits), self.V, self.V, _ptr(self.am), _ptr(self.meta),
                                          float(self.sample_temperature), int(self.sample_top_k), float(self.sample_top_p),
                                          _ptr(self.rng_state), _ptr(self.dec_dev),
                                          _ptr(getattr(self, "debug_uniforms", None))),

@@ -19,7 +19,7 @@ ATOL_MAX, ATOL_MEAN = 2e-2, 2e-3
 IMPLS = [int(x) for x in os.environ.get("LADE_TEST_ATTN_IMPLS", "2,1").split(",")]   # 2 = tcgen05 (product default), 1 = mma.sync fallback
 
 
-def run_kernel(q, k, v, lay, meta_vals, q_pad, n_splits, impl, kv_capacity=None):
+def run_kernel(q, k, v, lay, meta_vals, q_pad, n_splits, impl, kv_capacity=None, dt=torch.bfloat16):
     """q [Hq, q_len, D], k/v [Hkv, T, D] (cache incl. step rows). Returns [q_len, Hq*D].
     The visibility bitmask handed to the kernel comes from the ORACLE's predicate (independent of the CUDA one)."""
     from lookaheaddecoding_b200 import _cabi
@@ -28,12 +28,12 @@ def run_kernel(q, k, v, lay, meta_vals, q_pad, n_splits, impl, kv_capacity=None)
     Hkv, T, _ = k.shape
     cap = kv_capacity or (T + 70)
     dev = "cuda"
-    qb = torch.zeros(Hq, q_pad, D, dtype=torch.bfloat16, device=dev)
+    qb = torch.zeros(Hq, q_pad, D, dtype=dt, device=dev)
     qb[:, :q_len] = q
-    kc = torch.full((Hkv, cap, D), float("nan"), dtype=torch.bfloat16, device=dev)   # stale rows must never leak
-    vc = torch.full((Hkv, cap, D), float("nan"), dtype=torch.bfloat16, device=dev)
+    kc = torch.full((Hkv, cap, D), float("nan"), dtype=dt, device=dev)   # stale rows must never leak
+    vc = torch.full((Hkv, cap, D), float("nan"), dtype=dt, device=dev)
     kc[:, :T], vc[:, :T] = k, v
-    out = torch.zeros(q_pad, Hq * D, dtype=torch.bfloat16, device=dev)
+    out = torch.zeros(q_pad, Hq * D, dtype=dt, device=dev)
     meta = torch.zeros(_cabi.META_INTS, dtype=torch.int32, device=dev)
     for key, val in meta_vals.items():
         meta[key] = val
@@ -45,7 +45,8 @@ def run_kernel(q, k, v, lay, meta_vals, q_pad, n_splits, impl, kv_capacity=None)
     rowmask = torch.from_numpy(words.view(np.int32).copy()).to(dev)
     nbytes = lib.lade_attn_scratch_bytes(q_pad, Hq, D, n_splits)
     scratch = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
-    _cabi.check(lib.lade_attn_fwd(torch.cuda.current_stream().cuda_stream, qb.data_ptr(), kc.data_ptr(), vc.data_ptr(),
+    fwd = lib.lade_attn_fwd if dt == torch.bfloat16 else lib.lade_attn_fwd_f16
+    _cabi.check(fwd(torch.cuda.current_stream().cuda_stream, qb.data_ptr(), kc.data_ptr(), vc.data_ptr(),
                                   out.data_ptr(), 0 if lay.is_prefill else rowmask.data_ptr(), mw, meta.data_ptr(),
                                   scratch.data_ptr(), q_pad, Hq, Hkv, D, cap, T, n_splits, impl), "lade_attn_fwd")
     torch.cuda.synchronize()
@@ -172,3 +173,26 @@ def test_attention_head_dim_64_vs_oracle(kv_len, Hq, Hkv, splits):
     rc = lib.lade_attn_fwd(0, z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), 0, 0, z.data_ptr(), z.data_ptr(), 8, 2, 2, 64,
                            16, 16, 1, 2)
     assert rc == _cabi.LADE_EUNSUPPORTED          # the tcgen05 kernel refuses head_dim 64 when forced
+
+
+@pytest.mark.parametrize("kv_len,D,Hq,Hkv,splits", [(0, 128, 2, 2, 1), (300, 128, 4, 2, 3), (130, 64, 4, 2, 2)])
+def test_attention_fp16_vs_oracle(kv_len, D, Hq, Hkv, splits):
+    """fp16 models: lade_attn_fwd_f16 (mma.sync kernel on __half) against the reference's eager attention restated in
+    fp16; same tolerance in absolute terms (fp16 carries 3 more mantissa bits than bf16)."""
+    torch.manual_seed(kv_len + D)
+    W, N, g = 15, 5, 5
+    gs = N - 1
+    lay = LA.layout_from_shape([W - 1] + [W] * (N - 2), 1, g * gs, gs)
+    q_len = lay.q_len
+    T = kv_len + q_len
+    q = torch.randn(Hq, q_len, D, device="cuda").to(torch.float16)
+    k = torch.randn(Hkv, T, D, device="cuda").to(torch.float16)
+    v = torch.randn(Hkv, T, D, device="cuda").to(torch.float16)
+    q_pad = gs * (W + g) + 4
+    vis = torch.from_numpy(LA.step_mask(lay)).cuda()
+    mask = LR.additive_mask(vis, kv_len, torch.float16)
+    want = LR.eager_attention(q, k, v, mask, Hq // Hkv).transpose(0, 1).reshape(q_len, -1)
+    for impl in (0, 1):
+        out = run_kernel(q, k, v, lay, meta_for(lay, kv_len, q_pad), q_pad, splits, impl, dt=torch.float16)
+        assert out.dtype == torch.float16
+        check_close(out, want)

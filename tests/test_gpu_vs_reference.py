@@ -46,9 +46,11 @@ CASES = [("cfg1_w5n3g3",       TINY, 5,  3, 3,  64, 96, False),
          ("edge_n3_w20g20",    TINY, 20, 3, 20, 24, 48, True)]
 
 
-def build_pair(shape, seed=0):
+def build_pair(shape, seed=0, dtype=torch.bfloat16):
     from bench import build_model
     hf = build_model(shape, torch.device("cuda"), seed=seed)
+    if dtype != torch.bfloat16:
+        hf = hf.to(dtype)
     return hf, PAR.reference_model_sharing_weights(hf, shape)
 
 
@@ -131,3 +133,27 @@ def test_window_fill_step_larger_than_steady_and_host_stopping_criteria():
     finally:
         lade.restore_generate()
         os.environ["USE_LADE"] = "0"
+
+
+@pytest.mark.parametrize("name,shape,W,N,G,P,new,pool", [c for c in CASES if c[0] in ("cfg1_w5n3g3_pool", "w15n5g15", "gqa_w15n5g15",
+                                                                                     "d64_gqa_w15n5g15", "edge_p1")],
+                         ids=lambda v: v if isinstance(v, str) else None)
+def test_fp16_engine_ids_match_reference_on_the_same_gpu(name, shape, W, N, G, P, new, pool):
+    """fp16 models (the dtype of the reference's README / minimal.py): the *_f16 kernels against the unmodified reference
+    running in fp16 on the same GPU and weights; ties are measured in fp16 ulps."""
+    hf, ref = build_pair(shape, dtype=torch.float16)
+    assert next(ref.parameters()).dtype == torch.float16
+    g = torch.Generator().manual_seed(1)
+    prompt = torch.randint(3, shape["vocab"], (P,), generator=g).tolist()
+    ref_ids, ref_steps = PAR.reference_greedy(ref, prompt, new, W, N, G, py_seed=0, pool_from_prompt=pool)
+    eng, gen = engine_generate(hf, W, N, G, pool, P + new)
+    assert eng.dt == torch.float16
+    rep = PAR.compare_ids(gen, ref_ids, P, ref)
+    print(f"\nfp16 {name}: exact={rep['exact']} exact_prefix={rep['exact_prefix_tokens']}/{rep['compared_tokens']} "
+          f"divergences={rep['n_divergences']} worst={rep['worst_candidate_below_top_ulps']} ulp(fp16) ref_steps={ref_steps}")
+    assert rep["ok"], rep
+    # sampling on the fp16 logits (device verification): reproducible, in range
+    a = eng.generate(prompt, min(new, 24), rng=random.Random(1), sampling={"temperature": 0.8, "top_k": 40, "seed": 5})
+    b = eng.generate(prompt, min(new, 24), rng=random.Random(1), sampling={"temperature": 0.8, "top_k": 40, "seed": 5})
+    assert a == b and all(0 <= t < shape["vocab"] for t in a)
+    eng.close()
