@@ -166,7 +166,7 @@ class ClockSampler:
                 "source": "nvml" if self._nv is not None else "nvidia-smi"}
 
 
-def build_model(shape, device, seed=0, weights="random"):
+def build_model(shape, device, seed=0, weights="random", dtype=None):
     """HF LlamaForCausalLM of `shape`, random init normal(0, 0.02) (modeling_llama.py:934-943), bf16.
     weights="cyclic": o_proj and down_proj are zeroed, so every layer is the identity on the residual stream and the
     next token is a deterministic function of the last one -- the text becomes periodic, n-grams repeat, and the
@@ -199,6 +199,10 @@ def build_model(shape, device, seed=0, weights="random"):
             re.inv_freq = inv.to(device)
             if hasattr(re, "original_inv_freq"):
                 re.original_inv_freq = inv.to(device)
+    if dtype is not None:
+        import torch as _t
+        if dtype != _t.bfloat16:
+            model = model.to(dtype)              # same draws, rounded to the other 16-bit format
     model.eval()
     model.generation_config.pad_token_id = 0
     model.generation_config.eos_token_id = None
@@ -485,7 +489,7 @@ def time_generates(run_once, n, P, eng, dev):
     return toks, steps, e0.elapsed_time(e1)
 
 
-def extra_workload(name, args, dev, do_sample=False, model=None, reps=3):
+def extra_workload(name, args, dev, do_sample=False, model=None, reps=3, dtype=None):
     """One more BASELINE.json config measured in the same process (device-timed generate() calls + its own attention
     roofline): configs[2] (7B sampling, T=0.8) and configs[3] (CodeLlama-13B shape, W20 N7 G20)."""
     import torch
@@ -493,7 +497,7 @@ def extra_workload(name, args, dev, do_sample=False, model=None, reps=3):
     shape, W, N, G, P = WORKLOADS[name]
     own = model is None
     if own:
-        model = build_model(shape, dev)
+        model = build_model(shape, dev, dtype=dtype)
     eng = LookaheadEngine(model, W, N, G, max_total_len=P + args.max_new)
     torch.manual_seed(1)
     prompt = torch.randint(3, shape["vocab"], (1, P))[0].tolist()
@@ -507,7 +511,8 @@ def extra_workload(name, args, dev, do_sample=False, model=None, reps=3):
         run_once()
     toks, steps, ms = time_generates(run_once, reps, P, eng, dev)
     roof = attn_roofline(eng, shape)
-    rep = {"workload": f"{WORKLOAD_NAMES[name]}{' -> sampling temp=0.8 top_k=0 top_p=1.0' if do_sample else ''}, W={W} N={N} "
+    wname = WORKLOAD_NAMES[name] if dtype is None else WORKLOAD_NAMES[name].replace("bf16", str(dtype).replace("torch.", ""))
+    rep = {"workload": f"{wname}{' -> sampling temp=0.8 top_k=0 top_p=1.0' if do_sample else ''}, W={W} N={N} "
                        f"G={G}, prompt {P}, {args.max_new} new tokens", "value": round(toks / (ms * 1e-3), 2),
            "unit": "tokens/s", "generates_timed": reps, "ms_per_decode_step": round(ms / steps, 4),
            "accepted_tokens_per_step": round(toks / steps, 3), "attn_splits": eng.attn_splits, "roofline": roof}
@@ -768,7 +773,8 @@ def main():
 
     # ---- BASELINE.json configs[2] (7B sampling) and configs[3] (13B W20 N7 G20) in the same run
     if world == 1 and args.workload == "7b" and not args.do_sample and not args.no_extras and args.weights == "random":
-        for key, kw in (("7b_sampling", dict(name="7b", do_sample=True, model=model)), ("13b", dict(name="13b"))):
+        for key, kw in (("7b_sampling", dict(name="7b", do_sample=True, model=model)), ("13b", dict(name="13b")),
+                        ("7b_fp16", dict(name="7b", dtype=torch.float16))):     # the dtype of the reference's README / minimal.py
             try:
                 extras[key] = extra_workload(args=args, dev=dev, **kw)
             except Exception as ex:

@@ -177,8 +177,8 @@ def test_attention_head_dim_64_vs_oracle(kv_len, Hq, Hkv, splits):
 
 @pytest.mark.parametrize("kv_len,D,Hq,Hkv,splits", [(0, 128, 2, 2, 1), (300, 128, 4, 2, 3), (130, 64, 4, 2, 2)])
 def test_attention_fp16_vs_oracle(kv_len, D, Hq, Hkv, splits):
-    """fp16 models: lade_attn_fwd_f16 (mma.sync kernel on __half) against the reference's eager attention restated in
-    fp16; same tolerance in absolute terms (fp16 carries 3 more mantissa bits than bf16)."""
+    """fp16 models: lade_attn_fwd_f16 (impl 0: tcgen05 kernel on fp16 operands for head_dim 128, mma.sync for 64; impl 1:
+    mma.sync) against the reference's eager attention restated in fp16; same absolute tolerance as bf16."""
     torch.manual_seed(kv_len + D)
     W, N, g = 15, 5, 5
     gs = N - 1
