@@ -109,6 +109,14 @@ class LookaheadEngine:
             raise LadeError(f"head_dim {self.D} unsupported (attention kernels are instantiated for 128 and 64)")
         self.max_pos = int(getattr(cfg, "max_position_embeddings", 4096))
         rp = getattr(cfg, "rope_parameters", None) or {}
+        rope_type = (rp.get("rope_type") if isinstance(rp, dict) else None) or "default"
+        legacy = getattr(cfg, "rope_scaling", None)
+        if isinstance(legacy, dict) and (legacy.get("rope_type") or legacy.get("type") or "default") != "default":
+            rope_type = legacy.get("rope_type") or legacy.get("type")
+        if rope_type != "default":
+            # the reference knows "linear" / "dynamic" NTK scaling (modeling_llama.py:271-318); neither is wired into the
+            # device RoPE tables here, and silently decoding with unscaled positions would be wrong
+            raise LadeError(f"rope scaling '{rope_type}' is not supported (only the default rotary embedding)")
         self.rope_theta = float(rp.get("rope_theta", getattr(cfg, "rope_theta", 10000.0)) if isinstance(rp, dict)
                                 else getattr(cfg, "rope_theta", 10000.0))
         self.attn_impl = attn_impl
