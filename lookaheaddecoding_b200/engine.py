@@ -179,8 +179,10 @@ class LookaheadEngine:
         with torch.no_grad():
             for li, layer in enumerate(m.layers):
                 a, mlp = layer.self_attn, layer.mlp
-                if getattr(a.q_proj, "bias", None) is not None:
+                if any(getattr(m_, "bias", None) is not None for m_ in (a.q_proj, a.k_proj, a.v_proj, a.o_proj)):
                     raise LadeError("attention_bias=True is not supported")
+                if any(getattr(m_, "bias", None) is not None for m_ in (mlp.gate_proj, mlp.up_proj, mlp.down_proj)):
+                    raise LadeError("mlp_bias=True is not supported")
                 nq, nk = a.q_proj.weight.shape[0], a.k_proj.weight.shape[0]
                 qkv = gu = None
                 if prev is not None and li < len(prev[0]):
