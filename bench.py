@@ -246,15 +246,15 @@ def attn_roofline(eng, shape, reps=5):
     for k, v in {_cabi.M_Q_LEN: q_len, _cabi.M_KV_LEN: kv_len, _cabi.M_N_INPUT: 1, _cabi.M_TINY: W,
                  _cabi.M_N_LEVELS: N - 1, _cabi.M_N_GUESS_TOK: G * GS, _cabi.M_PHASE: 2, _cabi.M_Q_PAD: rows}.items():
         meta[k] = v
-    qb = torch.randn(eng.nh, rows, eng.D, device=eng.dev).to(torch.bfloat16)
-    attn_out = torch.empty(rows, eng.nh * eng.D, dtype=torch.bfloat16, device=eng.dev)
+    qb = torch.randn(eng.nh, rows, eng.D, device=eng.dev).to(eng.dt)
+    attn_out = torch.empty(rows, eng.nh * eng.D, dtype=eng.dt, device=eng.dev)
     scratch = torch.zeros(int(lib.lade_attn_scratch_bytes(rows, eng.nh, eng.D, eng.attn_splits)), dtype=torch.uint8, device=eng.dev)
     stream = torch.cuda.current_stream(eng.dev)
 
     def one_pass():
         cs = torch.cuda.current_stream(eng.dev).cuda_stream
         for l in range(eng.L):
-            _cabi.check(lib.lade_attn_fwd(cs, qb.data_ptr(), eng.kv[l, 0].data_ptr(), eng.kv[l, 1].data_ptr(),
+            _cabi.check(eng.k_attn_fwd(cs, qb.data_ptr(), eng.kv[l, 0].data_ptr(), eng.kv[l, 1].data_ptr(),
                                           attn_out.data_ptr(), rowmask.data_ptr(), mw, meta.data_ptr(),
                                           scratch.data_ptr(), rows, eng.nh, eng.nkv, eng.D, eng.kv_capacity,
                                           eng.kv_capacity, eng.attn_splits, eng.attn_impl))
