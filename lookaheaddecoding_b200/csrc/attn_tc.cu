@@ -31,7 +31,8 @@ constexpr int TC_TILE_BYTES = 128 * 128 * 2;   // one [128 x 128] bf16 tile = tw
 constexpr int TC_HALF_BYTES = TC_TILE_BYTES / 2;
 constexpr int TC_XCH_FLOATS = 512;   // 2 KB: row maxima (bf16 [2][4][128]) / row sums (fp32 [4][128]) of the 4 threads of a row
 constexpr int TC_SMEM_TILES = TC_TILE_BYTES * (1 + 2 * TC_STAGES);
-constexpr int TC_SMEM_BYTES = TC_SMEM_TILES + 256 + TC_XCH_FLOATS * 4;
+constexpr int TC_ONES_OFFSET = TC_SMEM_TILES + 256 + TC_XCH_FLOATS * 4;   // 512 B of 1.0: B operand of the row-sum MMA
+constexpr int TC_SMEM_BYTES = TC_ONES_OFFSET + 512;
 constexpr float TC_LOG2E = 1.4426950408889634f;
 // DSMEM merge transport (merge_mode 1): slots in the owner's dead K/V stages, (m, l) in its dead Q tile
 constexpr int TC_SO_STRIDE = 132;                       // floats per staged O row (528 B: conflict-free float4 rows)
@@ -53,13 +54,14 @@ enum { TS_START = 0, TS_KFULL0 = 1, TS_SFULL0 = 2, TS_OFINAL = 3, TS_STAGED = 4,
 // ---- kernel ---------------------------------------------------------------------------------------------
 // grid (n_splits, heads, q tiles); when n_splits > 1 the n_splits CTAs of one (head, q tile) form a thread-block
 // cluster and merge their split-KV partials through distributed shared memory.
-template <typename ET>
+template <typename ET, bool ROWSUM_MMA>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, ET* __restrict__ out,
                    const uint32_t* __restrict__ rowmask, int mask_words, const int* __restrict__ meta, int q_pad,
                    int n_heads, int n_kv_heads, int n_splits, float inv_sqrt_d, float* __restrict__ part_o,
                    float2* __restrict__ part_ml, int merge_mode) {
+  constexpr bool rowsum_mma = ROWSUM_MMA;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int split = blockIdx.x, h = blockIdx.y, mt = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -133,12 +135,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int j = n_old; j < n_pre; ++j) issue_tile(j);
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (rowsum_mma && threadIdx.x >= 64 && threadIdx.x < 64 + 128) {       // 256 x (1.0, 1.0) pairs of the model dtype
+      reinterpret_cast<uint32_t*>(smem + TC_ONES_OFFSET)[threadIdx.x - 64] = Elem<ET>::pack2(1.f, 1.f);
+      fence_proxy_async();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
   }
   const uint32_t tmem_base = active ? *tmem_slot : 0u;
   const uint32_t tmem_O = tmem_base + 256;
+  const uint32_t tmem_L = tmem_base + 384;      // row sums by tensor core (rowsum_mma): 16 equal columns, column 0 is read
   // a softmax thread's share of its split's result: 32 fp32 of the unnormalised O row + the row's (max, sum);
   // they stay in registers across the role join for the split merge at the end of the kernel
   float ov[32];
@@ -198,6 +205,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const uint64_t da = umma_desc(sK_a(s) + (kk >> 2) * TC_HALF_BYTES + (kk & 3) * 32, 16, 1024);
           const uint64_t db = umma_desc(sV_a(s) + kk * 2048, TC_HALF_BYTES, 1024);
           umma_bf16(tmem_O, da, db, IDESC_PV, (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        if (rowsum_mma) {
+          // row sums on the tensor core: L += P x ones[128 kv x 16] (every element 1.0, so only the footprint of the
+          // B operand matters: 4 core matrices = 512 B), which takes the 32 adds per thread and tile off the FMA pipe
+          // and makes the normaliser the sum of the ROUNDED probabilities
+          constexpr uint32_t IDESC_L = umma_idesc_n(16u, false, sizeof(ET) == 2 && !std::is_same<ET, __nv_bfloat16>::value);
+          const uint64_t dones = umma_desc_noswizzle(sQ_a + TC_ONES_OFFSET, 128, 256);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint64_t da = umma_desc(sK_a(s) + (kk >> 2) * TC_HALF_BYTES + (kk & 3) * 32, 16, 1024);
+            umma_bf16(tmem_L, da, dones, IDESC_L, (j > 0 || kk > 0) ? 1u : 0u);
+          }
         }
         umma_commit(BAR(B_FREE + s));
         if (j == my_tiles - 1) umma_commit(BAR(B_OFINAL));
@@ -260,10 +279,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const float scale = (m_new == -INFINITY) ? 1.f : exp2f((m_used - m_new) * TC_LOG2E);
           l_sum *= scale;
           tmem_ld32(tO, ov);                         // my quarter of the O columns
+          float lv = 0.f;
+          if (rowsum_mma && q4 == 0) lv = tmem_ld1(tmem_L + lane_addr);      // ... and the row's running sum
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) ov[i] *= scale;
           tmem_st32(tO, ov);
+          if (rowsum_mma && q4 == 0) tmem_st1(tmem_L + lane_addr, lv * scale);
           tmem_st_wait();
           m_used = m_new;
         }
@@ -289,7 +311,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             round_scale_round2<ET>(v[i], v[i + 1], inv_sqrt_d, r0, r1);
             p[e] = ex2_approx(r0 * TC_LOG2E - off);
             p[e + 1] = ex2_approx(r1 * TC_LOG2E - off);
-            ps4[g] += p[e] + p[e + 1];
+            if (!rowsum_mma) ps4[g] += p[e] + p[e + 1];
           }
           uint4 pk;
           pk.x = Elem<ET>::pack2(p[0], p[1]); pk.y = Elem<ET>::pack2(p[2], p[3]);
@@ -308,7 +330,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             round_scale_round2<ET>(v[i], v[i + 1], inv_sqrt_d, r0, r1);
             p[e] = ((mb >> i) & 1u) ? ex2_approx(r0 * TC_LOG2E - off) : 0.f;
             p[e + 1] = ((mb >> (i + 1)) & 1u) ? ex2_approx(r1 * TC_LOG2E - off) : 0.f;
-            ps4[g] += p[e] + p[e + 1];
+            if (!rowsum_mma) ps4[g] += p[e] + p[e + 1];
           }
           uint4 pk;
           pk.x = Elem<ET>::pack2(p[0], p[1]); pk.y = Elem<ET>::pack2(p[2], p[3]);
@@ -317,7 +339,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           *reinterpret_cast<uint4*>(prow + ((cc ^ (row_l & 7)) << 4)) = pk;
         }
       }
-      l_sum += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
+      if (!rowsum_mma) l_sum += (ps4[0] + ps4[1]) + (ps4[2] + ps4[3]);
       if (j == 1) TC_STAMP(13, 64);
       // stale cache rows past T must not reach the PV MMA (0 * NaN): zero them in the staged V tile
       const int tile0 = (tile_lo + j) * TC_BN;
@@ -343,10 +365,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(BAR(B_OFINAL), 0);
     tc_fence_after();
     TC_STAMP(TS_OFINAL, 64);
-    named_bar_sync(1, TC_SOFTMAX_THREADS);          // the max-exchange slots are free again
-    s_xsum[q4 * 128 + row_l] = l_sum;
-    named_bar_sync(1, TC_SOFTMAX_THREADS);
-    l_sum = (s_xsum[row_l] + s_xsum[128 + row_l]) + (s_xsum[256 + row_l] + s_xsum[384 + row_l]);
+    if (rowsum_mma) {
+      l_sum = tmem_ld1(tmem_L + lane_addr);         // every thread of the row reads the row's sum
+    } else {
+      named_bar_sync(1, TC_SOFTMAX_THREADS);        // the max-exchange slots are free again
+      s_xsum[q4 * 128 + row_l] = l_sum;
+      named_bar_sync(1, TC_SOFTMAX_THREADS);
+      l_sum = (s_xsum[row_l] + s_xsum[128 + row_l]) + (s_xsum[256 + row_l] + s_xsum[384 + row_l]);
+    }
     tmem_ld32(tO, ov);
     tmem_ld_wait();
     m_row = m_used;
@@ -585,6 +611,15 @@ static int merge_mode() {          // default: DSMEM push (1); LADE_ATTN_MERGE=l
   return v;
 }
 
+static int rowsum_mode() {         // LADE_ATTN_ROWSUM=mma: row sums by an extra N=16 MMA against a ones tile (default: fp32 adds)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LADE_ATTN_ROWSUM");
+    v = (e && e[0] == 'm') ? 1 : 0;
+  }
+  return v;
+}
+
 static int g_pdl_override = -1;      // lade_debug_attn_pdl: -1 = environment (LADE_PDL), 0 / 1 = forced
 int attn_tc_set_pdl(int v) { g_pdl_override = v < 0 ? -1 : (v ? 1 : 0); return LADE_OK; }
 
@@ -618,7 +653,8 @@ static int attn_fwd_tc_launch_t(cudaStream_t stream, const void* q, const void* 
   int cur_dev = 0;
   LADE_CUDA_CHECK(cudaGetDevice(&cur_dev));
   if (!((attr_devs >> (cur_dev & 63)) & 1ull)) {
-    LADE_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel<ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    LADE_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel<ET, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    LADE_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_kernel<ET, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     attr_devs |= 1ull << (cur_dev & 63);
   }
   cudaLaunchConfig_t cfg = {};
@@ -641,8 +677,11 @@ static int attn_fwd_tc_launch_t(cudaStream_t stream, const void* q, const void* 
   // scratch (lade_attn_scratch_bytes): [64 KB reserved][partial O: n_splits * n_heads * rows_pad * D fp32][(m, l) per row]
   float* part_o = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 65536);
   float2* part_ml = reinterpret_cast<float2*>(part_o + (size_t)n_splits * n_heads * q_tiles * TC_BM * TC_D);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_fwd_tc_kernel<ET>, tmQ, tmK, tmV, (ET*)out, rowmask, mask_words, meta,
-                                     q_pad, n_heads, n_kv_heads, n_splits, inv_sqrt_d, part_o, part_ml, merge_mode());
+  cudaError_t e = rowsum_mode()
+      ? cudaLaunchKernelEx(&cfg, attn_fwd_tc_kernel<ET, true>, tmQ, tmK, tmV, (ET*)out, rowmask, mask_words, meta,
+                           q_pad, n_heads, n_kv_heads, n_splits, inv_sqrt_d, part_o, part_ml, merge_mode())
+      : cudaLaunchKernelEx(&cfg, attn_fwd_tc_kernel<ET, false>, tmQ, tmK, tmV, (ET*)out, rowmask, mask_words, meta,
+                           q_pad, n_heads, n_kv_heads, n_splits, inv_sqrt_d, part_o, part_ml, merge_mode());
   if (e != cudaSuccess) { set_cuda_error(e, "cudaLaunchKernelEx(attn_fwd_tc_kernel)"); return LADE_ECUDA; }
   return LADE_OK;
 }
