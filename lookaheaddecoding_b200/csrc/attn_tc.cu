@@ -611,11 +611,11 @@ static int merge_mode() {          // default: DSMEM push (1); LADE_ATTN_MERGE=l
   return v;
 }
 
-static int rowsum_mode() {         // LADE_ATTN_ROWSUM=mma: row sums by an extra N=16 MMA against a ones tile (default: fp32 adds)
-  static int v = -1;
+static int rowsum_mode() {         // default: row sums by an extra N=16 MMA against a ones tile; LADE_ATTN_ROWSUM=add: fp32 adds
+  static int v = -1;                 // same-box A/B (profiles/r02_attn_rowsum_ab.jsonl): 15.0 vs 15.2 us at the bench shape, 21.9 vs 22.5 at kv=3072
   if (v < 0) {
     const char* e = getenv("LADE_ATTN_ROWSUM");
-    v = (e && e[0] == 'm') ? 1 : 0;
+    v = (e && e[0] == 'a') ? 0 : 1;
   }
   return v;
 }
