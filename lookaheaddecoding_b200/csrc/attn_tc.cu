@@ -1,14 +1,17 @@
 // Lookahead attention, Blackwell-native path (impl=2): TMA-staged K/V tiles, tcgen05.mma with TMEM
-// accumulators, one softmax thread per query row, split-KV with an in-kernel combine.
+// accumulators, four softmax threads per query row, split-KV across a thread-block cluster with an in-kernel merge.
 //
-// Per CTA: one (head, 128-row query tile, KV split).  Warp roles (192 threads):
-//   warp 0      TMA producer   Q tile + a STAGES-deep ring of K/V tiles (128 kv rows x 128 d, SWIZZLE_128B)
-//   warp 1      MMA issuer     S = Q K^T  (kind::f16, M=128 N=128 K=16 x8, both operands K-major)
-//                              O += P V   (A = P K-major from smem, B = V MN-major from smem), TMEM alloc
-//   warps 2..9  softmax        two threads per query row (TMEM lane), each owning 64 of the tile's 128 kv
-//                              columns: tcgen05.ld -> reference rounding -> lookahead mask bits in registers
-//                              -> exp2 -> P (bf16, swizzled into the K tile's smem) ; lazy O rescale in TMEM
-// TMEM: S double buffer (2 x 128 cols) + O (128 cols).
+// Per CTA: one (head, 128-row query tile, KV split).  Warp roles (576 threads):
+//   warp 0       TMA producer   Q tile + a 3-deep (long launches) or 2-deep (short launches) ring of K/V tiles
+//                               (128 kv rows x 128 d, SWIZZLE_128B)
+//   warp 1       MMA issuer     S = Q K^T  (kind::f16, M=128 N=128 K=16 x8, both operands K-major)
+//                               O += P V   (A = P K-major from smem, B = V MN-major from smem), L += P 1 (row sums),
+//                               TMEM alloc
+//   warps 2..17  softmax        four threads per query row (TMEM lane), each owning 32 of the tile's 128 kv
+//                               columns: tcgen05.ld -> reference rounding -> lookahead mask bits in registers
+//                               -> exp2 -> P (model dtype, swizzled into the K tile's smem); lazy O rescale in TMEM
+// TMEM: S double buffer (2 x 128 cols) + O (128 cols) + L (16 cols).
+// Split merge: fp32 partial rows pushed from registers into the owner CTA's shared memory (st.shared::cluster).
 //
 // Numerics follow attn_mma.cu / the reference (lade/models/modeling_llama.py:520-541); the mask is the
 // same register predicate (common.cuh row_sees == modeling_llama.py:115-207).
@@ -24,20 +27,21 @@ namespace lade {
 constexpr int TC_BM = 128;
 constexpr int TC_BN = 128;
 constexpr int TC_D = 128;
-constexpr int TC_STAGES = 3;
+constexpr int TC_MAX_STAGES = 3;   // shared memory is sized for 3 K/V stages; the 2-stage instantiation turns the third into merge slots
 constexpr int TC_SOFTMAX_THREADS = 512;            // 16 warps: 4 threads per query row
 constexpr int TC_THREADS = 64 + TC_SOFTMAX_THREADS;
 constexpr int TC_TILE_BYTES = 128 * 128 * 2;   // one [128 x 128] bf16 tile = two [128 x 64] swizzle blocks
 constexpr int TC_HALF_BYTES = TC_TILE_BYTES / 2;
 constexpr int TC_XCH_FLOATS = 512;   // 2 KB: row maxima (bf16 [2][4][128]) / row sums (fp32 [4][128]) of the 4 threads of a row
-constexpr int TC_SMEM_TILES = TC_TILE_BYTES * (1 + 2 * TC_STAGES);
+constexpr int TC_SMEM_TILES = TC_TILE_BYTES * (1 + 2 * TC_MAX_STAGES);
 constexpr int TC_ONES_OFFSET = TC_SMEM_TILES + 256 + TC_XCH_FLOATS * 4;   // 512 B of 1.0: B operand of the row-sum MMA
 constexpr int TC_SMEM_BYTES = TC_ONES_OFFSET + 512;
 constexpr float TC_LOG2E = 1.4426950408889634f;
-// DSMEM merge transport (merge_mode 1): slots in the owner's dead K/V stages, (m, l) in its dead Q tile
+// DSMEM merge transport (merge_mode 1).  3 stages: slots alias the owner's dead K/V stages, (m, l) its dead Q tile (a
+// cluster barrier separates compute from the pushes).  2 stages: the third stage's 64 KB are DEDICATED slots
+// ((n - 1) * ceil(128 / n) * 528 B <= 60,192 for n <= 8, then (m, l)), so a split pushes the moment it is done.
 constexpr int TC_SO_STRIDE = 132;                       // floats per staged O row (528 B: conflict-free float4 rows)
-constexpr int TC_SO_OFFSET = TC_TILE_BYTES;
-constexpr int TC_SML_OFFSET = 0;
+constexpr int TC_SLOT_ML_OFFSET = 60416;                // (m, l) table inside the dedicated slot region
 
 template <typename ET>
 __host__ __device__ constexpr uint32_t umma_idesc(bool b_mn_major) {
@@ -60,7 +64,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                    const __grid_constant__ CUtensorMap tmV, ET* __restrict__ out,
                    const uint32_t* __restrict__ rowmask, int mask_words, const int* __restrict__ meta, int q_pad,
                    int n_heads, int n_kv_heads, int n_splits, float inv_sqrt_d, float* __restrict__ part_o,
-                   float2* __restrict__ part_ml, int merge_mode) {
+                   float2* __restrict__ part_ml, int flags) {
   constexpr bool rowsum_mma = ROWSUM_MMA;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int split = blockIdx.x, h = blockIdx.y, mt = blockIdx.z;
@@ -82,6 +86,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int my_tiles = active ? t_base + (split < t_rem ? 1 : 0) : 0;
   const int hk = h / (n_heads / n_kv_heads);
   const int HD = n_heads * TC_D;
+  // K/V ring depth.  Short split-KV launches (no split holds more than (flags >> 8) tiles: the decode step at the
+  // benchmark's context) run a 2-deep ring and turn the third stage into DEDICATED merge slots: a split then pushes
+  // its partial the moment it is done -- the early finishers while the longest split still computes -- and the
+  // compute/push cluster barrier of the aliasing layout goes away.  Long launches keep 3 stages (the stream needs them).
+  const int merge_mode = flags & 1;
+  const int nst = (n_splits > 1 && merge_mode == 1 && t_base + (t_rem ? 1 : 0) <= ((flags >> 8) & 0xff)) ? 2 : 3;
+  const int TC_SO_OFFSET = nst == 2 ? TC_TILE_BYTES * 5 : TC_TILE_BYTES;
+  const int TC_SML_OFFSET = nst == 2 ? TC_TILE_BYTES * 5 + TC_SLOT_ML_OFFSET : 0;
   long long* tbuf = g_attn_timing ? g_attn_timing + 16ll * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
   TC_STAMP(TS_START, 0);
   // programmatic dependent launch, producer side: a dependent grid (in the decode step: none -- the o_proj GEMM is a
@@ -94,8 +106,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   // barrier slots: 0 q_full | 1.. k_full[S] | v_full[S] | stage_free[S] | s_full[2] | p_full[2] | o_final
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  const int B_QFULL = 0, B_KFULL = 1, B_VFULL = 1 + TC_STAGES, B_FREE = 1 + 2 * TC_STAGES,
-            B_SFULL = 1 + 3 * TC_STAGES, B_PFULL = 3 + 3 * TC_STAGES, B_OFINAL = 5 + 3 * TC_STAGES;
+  const int B_QFULL = 0, B_KFULL = 1, B_VFULL = 1 + TC_MAX_STAGES, B_FREE = 1 + 2 * TC_MAX_STAGES,
+            B_SFULL = 1 + 3 * TC_MAX_STAGES, B_PFULL = 3 + 3 * TC_MAX_STAGES, B_OFINAL = 5 + 3 * TC_MAX_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
   ET* s_xmax = reinterpret_cast<ET*>(smem + TC_SMEM_TILES + 256);   // [2][4][128] row maxima (model dtype: exact)
   float* s_xsum = reinterpret_cast<float*>(smem + TC_SMEM_TILES + 256);                   // [4][128] row sums (epilogue)
@@ -107,7 +119,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (threadIdx.x == 0) {
       if ((sQ_a & 1023u) != 0) __trap();   // SWIZZLE_128B tiles need 1024-byte alignment
       mbar_init(BAR(B_QFULL), 1);
-      for (int s = 0; s < TC_STAGES; ++s) { mbar_init(BAR(B_KFULL + s), 1); mbar_init(BAR(B_VFULL + s), 1); mbar_init(BAR(B_FREE + s), 1); }
+      for (int s = 0; s < TC_MAX_STAGES; ++s) { mbar_init(BAR(B_KFULL + s), 1); mbar_init(BAR(B_VFULL + s), 1); mbar_init(BAR(B_FREE + s), 1); }
       for (int b = 0; b < 2; ++b) { mbar_init(BAR(B_SFULL + b), 1); mbar_init(BAR(B_PFULL + b), TC_SOFTMAX_THREADS / 32); }
       mbar_init(BAR(B_OFINAL), 1);
       fence_barrier_init();
@@ -124,7 +136,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tma_load_3d(sV_a(j), &tmV, BAR(B_VFULL + j), 0, row0, hk);
         tma_load_3d(sV_a(j) + TC_HALF_BYTES, &tmV, BAR(B_VFULL + j), 64, row0, hk);
       };
-      const int n_pre = my_tiles < TC_STAGES ? my_tiles : TC_STAGES;
+      const int n_pre = my_tiles < nst ? my_tiles : nst;
       int n_old = 0;                                   // leading tiles that hold only rows of earlier steps
       while (n_old < n_pre && (tile_lo + n_old + 1) * TC_BN <= kv_len) ++n_old;
       for (int j = 0; j < n_old; ++j) issue_tile(j);
@@ -143,6 +155,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncthreads();
     tc_fence_after();
   }
+  // 2-deep ring: the only thing a pusher must know about its target is that the CTA is resident (its slots are never
+  // used for anything else), so the cluster meets HERE, split-phase: arrive now, wait just before the first push
+  if (nst == 2) cluster_arrive();
   const uint32_t tmem_base = active ? *tmem_slot : 0u;
   const uint32_t tmem_O = tmem_base + 256;
   const uint32_t tmem_L = tmem_base + 384;      // row sums by tensor core (rowsum_mma): 16 equal columns, column 0 is read
@@ -156,9 +171,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   } else if (warp == 0) {
     // ================= TMA producer (tiles beyond the first STAGES; the rest was issued in the prologue) =====
     if (lane == 0) {
-      for (int j = TC_STAGES; j < my_tiles; ++j) {
-        const int s = j % TC_STAGES;
-        mbar_wait(BAR(B_FREE + s), ((j / TC_STAGES) - 1) & 1);
+      for (int j = nst; j < my_tiles; ++j) {
+        const int s = j % nst;
+        mbar_wait(BAR(B_FREE + s), ((j / nst) - 1) & 1);
         const int row0 = (tile_lo + j) * TC_BN;
         mbar_expect_tx(BAR(B_KFULL + s), TC_TILE_BYTES);
         tma_load_3d(sK_a(s), &tmK, BAR(B_KFULL + s), 0, row0, hk);
@@ -175,8 +190,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       constexpr uint32_t IDESC_QK = umma_idesc<ET>(false);
       constexpr uint32_t IDESC_PV = umma_idesc<ET>(true);
       auto issue_qk = [&](int j) {
-        const int s = j % TC_STAGES;
-        mbar_wait(BAR(B_KFULL + s), (j / TC_STAGES) & 1);
+        const int s = j % nst;
+        mbar_wait(BAR(B_KFULL + s), (j / nst) & 1);
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)(j & 1) * 128u;
 #pragma unroll
@@ -195,9 +210,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       issue_qk(0);
       for (int j = 0; j < my_tiles; ++j) {
         if (j + 1 < my_tiles) issue_qk(j + 1);
-        const int s = j % TC_STAGES;
+        const int s = j % nst;
         mbar_wait(BAR(B_PFULL + (j & 1)), (j >> 1) & 1);
-        mbar_wait(BAR(B_VFULL + s), (j / TC_STAGES) & 1);
+        mbar_wait(BAR(B_VFULL + s), (j / nst) & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
@@ -237,7 +252,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t tO = tmem_O + lane_addr + (uint32_t)q4 * 32u;
     float m_used = -INFINITY, l_sum = 0.f;
     for (int j = 0; j < my_tiles; ++j) {
-      const int buf = j & 1, s = j % TC_STAGES;
+      const int buf = j & 1, s = j % nst;
       if (j == 1) TC_STAMP(8, 64);
       mbar_wait(BAR(B_SFULL + buf), (j >> 1) & 1);
       tc_fence_after();
@@ -273,7 +288,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       } else {
         const bool need = (mx > m_used + 5.545177f) || (m_used == -INFINITY && mx > -INFINITY);
         if (__any_sync(0xffffffffu, need)) {
-          mbar_wait(BAR(B_FREE + (j - 1) % TC_STAGES), ((j - 1) / TC_STAGES) & 1);   // PV(j-1) landed in O
+          mbar_wait(BAR(B_FREE + (j - 1) % nst), ((j - 1) / nst) & 1);   // PV(j-1) landed in O
           tc_fence_after();
           const float m_new = fmaxf(m_used, mx);
           const float scale = (m_new == -INFINITY) ? 1.f : exp2f((m_used - m_new) * TC_LOG2E);
@@ -344,7 +359,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // stale cache rows past T must not reach the PV MMA (0 * NaN): zero them in the staged V tile
       const int tile0 = (tile_lo + j) * TC_BN;
       if (tile0 + TC_BN > T) {
-        mbar_wait(BAR(B_VFULL + s), (j / TC_STAGES) & 1);
+        mbar_wait(BAR(B_VFULL + s), (j / nst) & 1);
         if (tile0 + row_l >= T) {                   // V tile row == kv row; each quarter clears 64 of its 256 bytes
           unsigned char* pV = smem + TC_TILE_BYTES * (2 + 2 * s) + (q4 >> 1) * TC_HALF_BYTES + row_l * 128 + (q4 & 1) * 64;
           const uint4 z = make_uint4(0, 0, 0, 0);
@@ -411,7 +426,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   // its split's unnormalised O row (and the row's (m, l)) in registers; threads of owned rows keep theirs, the others
   // ship theirs to the owner, who combines:  w_s = 2^(m_s - m),  out = sum_s w_s O_s / sum_s w_s l_s.
   // Transport 0 (LADE_ATTN_MERGE=l2, kept for A/B): the split's slab of an L2-resident scratch + one cluster barrier.
-  const int per = (TC_BM + n_active - 1) / n_active;
+  // only the tile's real rows (row < q_pad) travel: the padding rows of the last q tile are neither pushed nor merged
+  const int rows_valid = min(TC_BM, q_pad - mt * TC_BM);
+  const int per = (rows_valid + n_active - 1) / n_active;
   int dest = -1;
   const long long hm = (long long)h * gridDim.z + mt;
   if (merge_mode == 1) {
@@ -422,16 +439,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // owner threads then combine their own registers with the slots from LOCAL shared memory.  Same-box A/B
     // (profiles/r02_attn_merge_ab.jsonl): 15.2 us per launch at the bench shape against 18.6 us for the L2 transport
     // below and 16.9 us for round 1's pull (stage locally, siblings read over DSMEM).
-    cluster_arrive();
+    if (nst != 2) cluster_arrive();
     cluster_wait();
     TC_STAMP(TS_CLUSTER, 0);
     int r_in = 0;
     if (active && warp >= 2) {
       const int row_l = (warp & 3) * 32 + lane;
       const int q4 = (warp - 2) >> 2;
-      dest = row_l / per;
+      dest = row_l < rows_valid ? row_l / per : -2;
       r_in = row_l - dest * per;
-      if (dest != split) {
+      if (dest >= 0 && dest != split) {
         const int slot = split < dest ? split : split - 1;
         const uint32_t o_a = dsmem_addr(sQ_a + TC_SO_OFFSET + (uint32_t)(((slot * per + r_in) * TC_SO_STRIDE + q4 * 32) * 4), dest);
 #pragma unroll
@@ -485,8 +502,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (active && warp >= 2) {
     const int row_l = (warp & 3) * 32 + lane;
     const int q4 = (warp - 2) >> 2;
-    dest = row_l / per;
-    if (dest != split) {
+    dest = row_l < rows_valid ? row_l / per : -2;
+    if (dest >= 0 && dest != split) {
       float4* dst = reinterpret_cast<float4*>(part_o + ((hm * n_splits + split) * TC_BM + row_l) * TC_D + q4 * 32);
 #pragma unroll
       for (int v4 = 0; v4 < 8; ++v4) dst[v4] = make_float4(ov[v4 * 4], ov[v4 * 4 + 1], ov[v4 * 4 + 2], ov[v4 * 4 + 3]);
@@ -620,6 +637,17 @@ static int rowsum_mode() {         // default: row sums by an extra N=16 MMA aga
   return v;
 }
 
+static int stage2_tiles() {        // 2-deep K/V ring + dedicated merge slots when no split holds more tiles than this (0 = never)
+  static int v = -1;                 // same-box A/B (profiles/r02_attn_stage2_ab.jsonl): -2 ... -2.5 % up to 4 tiles per split, +2 % at 5
+  if (v < 0) {
+    const char* e = getenv("LADE_ATTN_STAGE2_TILES");
+    v = e ? atoi(e) : 4;
+    if (v < 0) v = 0;
+    if (v > 255) v = 255;
+  }
+  return v;
+}
+
 static int g_pdl_override = -1;      // lade_debug_attn_pdl: -1 = environment (LADE_PDL), 0 / 1 = forced
 int attn_tc_set_pdl(int v) { g_pdl_override = v < 0 ? -1 : (v ? 1 : 0); return LADE_OK; }
 
@@ -679,9 +707,9 @@ static int attn_fwd_tc_launch_t(cudaStream_t stream, const void* q, const void* 
   float2* part_ml = reinterpret_cast<float2*>(part_o + (size_t)n_splits * n_heads * q_tiles * TC_BM * TC_D);
   cudaError_t e = rowsum_mode()
       ? cudaLaunchKernelEx(&cfg, attn_fwd_tc_kernel<ET, true>, tmQ, tmK, tmV, (ET*)out, rowmask, mask_words, meta,
-                           q_pad, n_heads, n_kv_heads, n_splits, inv_sqrt_d, part_o, part_ml, merge_mode())
+                           q_pad, n_heads, n_kv_heads, n_splits, inv_sqrt_d, part_o, part_ml, merge_mode() | (stage2_tiles() << 8))
       : cudaLaunchKernelEx(&cfg, attn_fwd_tc_kernel<ET, false>, tmQ, tmK, tmV, (ET*)out, rowmask, mask_words, meta,
-                           q_pad, n_heads, n_kv_heads, n_splits, inv_sqrt_d, part_o, part_ml, merge_mode());
+                           q_pad, n_heads, n_kv_heads, n_splits, inv_sqrt_d, part_o, part_ml, merge_mode() | (stage2_tiles() << 8));
   if (e != cudaSuccess) { set_cuda_error(e, "cudaLaunchKernelEx(attn_fwd_tc_kernel)"); return LADE_ECUDA; }
   return LADE_OK;
 }
