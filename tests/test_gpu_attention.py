@@ -104,6 +104,9 @@ def _oracle_attn(q, k, v, lay, kv_len):
     (0, 15, 5, 15, 2, 2, 1), (1, 15, 5, 15, 2, 2, 2), (63, 15, 5, 3, 4, 2, 2), (64, 15, 5, 15, 2, 2, 5),
     (1000, 15, 5, 15, 8, 8, 5), (3001, 15, 5, 0, 4, 4, 7), (517, 20, 7, 20, 4, 4, 3), (200, 5, 3, 3, 2, 1, 4),
     (130, 60, 8, 7, 2, 2, 2),
+    # more than 4 KV tiles per split: the 3-deep ring whose merge slots alias the K/V stages (shorter launches run
+    # the 2-deep ring with dedicated slots)
+    (3001, 15, 5, 15, 2, 2, 3), (2300, 15, 5, 15, 4, 2, 4),
 ])
 def test_attention_steady_shapes_vs_oracle(kv_len, W, N, g, Hq, Hkv, splits, impl):
     torch.manual_seed(kv_len + W)
