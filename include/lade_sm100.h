@@ -161,12 +161,17 @@ int lade_rope_append(void* stream, const void* qkv, const void* cos_tab, const v
  * dense mask of j_make_causal_mask_multilevel (:115-207) and flash_attn_lade.flash_attn_func(...,
  * lookahead=[...]) (:705-713).  `scratch` holds split-KV partials: lade_attn_scratch_bytes().
  * head_dim 128: tcgen05/TMA kernel (impl 0 or 2) or the mma.sync kernel (impl 1); head_dim 64 (TinyLlama-style): the
- * mma.sync kernel (impl 0 or 1).  Other head dimensions: LADE_EUNSUPPORTED. */
+ * mma.sync kernel (impl 0 or 1).  Other head dimensions: LADE_EUNSUPPORTED.
+ * impl 3 (head_dim 128): the tcgen05 kernel's REFERENCE-ORDER variant -- the probabilities are normalised by the sum
+ * of the whole row in fp32 and rounded to the model dtype afterwards, exactly the order of :530-541 (impl 2 is an online
+ * softmax: it rounds exp(x - max) before the sum is known, which changes the last bit of about half of the outputs).
+ * Every S tile of a KV split stays in tensor memory, so kv_bound must be a true bound of kv_len + q_len and at most
+ * 384 * n_splits (n_splits <= 8): LADE_EUNSUPPORTED otherwise.  Slower; a parity mode. */
 int lade_attn_fwd(void* stream, const void* q, const void* k_cache, const void* v_cache, void* out,
                   const uint32_t* rowmask, int32_t mask_words, const int32_t* meta, void* scratch, int32_t q_pad,
                   int32_t n_heads, int32_t n_kv_heads, int32_t head_dim, int32_t kv_capacity,
                   int32_t kv_bound /* host upper bound of kv_len + q_len */, int32_t n_splits,
-                  int32_t impl /* 0 = default (= 2), 1 = mma.sync path, 2 = tcgen05/TMA path */);
+                  int32_t impl /* 0 = default (= 2), 1 = mma.sync path, 2 = tcgen05/TMA path, 3 = its reference-order variant */);
 /* Bytes of zero-initialised scratch `lade_attn_fwd` needs for a shape (impl 1 keeps split partials there; the
  * tcgen05 path merges inside the cluster and only needs the buffer to exist).  No reference counterpart. */
 int64_t lade_attn_scratch_bytes(int32_t q_pad, int32_t n_heads, int32_t head_dim, int32_t n_splits);

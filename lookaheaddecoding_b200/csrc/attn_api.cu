@@ -8,6 +8,9 @@ int attn_fwd_mma_launch(cudaStream_t stream, const void* q, const void* k_cache,
 int attn_fwd_tc_launch(cudaStream_t stream, const void* q, const void* k_cache, const void* v_cache, void* out,
                        const uint32_t* rowmask, int mask_words, const int32_t* meta, void* scratch, int q_pad, int n_heads,
                        int n_kv_heads, int head_dim, int kv_capacity, int kv_bound, int n_splits, int is_f16);
+int attn_fwd_tc_exact_launch(cudaStream_t stream, const void* q, const void* k_cache, const void* v_cache, void* out,
+                             const uint32_t* rowmask, int mask_words, const int32_t* meta, void* scratch, int q_pad, int n_heads,
+                             int n_kv_heads, int head_dim, int kv_capacity, int kv_bound, int n_splits, int is_f16);
 int attn_tc_set_timing_buffer(void* dev_ptr);
 int attn_tc_set_pdl(int v);
 }  // namespace lade
@@ -34,7 +37,12 @@ int lade_attn_fwd(void* stream, const void* q, const void* k_cache, const void* 
   if (q_pad < 1 || n_heads < 1 || n_kv_heads < 1 || n_heads % n_kv_heads != 0 || n_splits < 1 || kv_capacity < 1)
     return LADE_EINVAL;
   // impl 0 = the library's choice: the Blackwell-native tcgen05/TMA kernel for head_dim 128, the mma.sync kernel for the
-  // other instantiated head dimension (64); impl 2 / 1 force one of them
+  // other instantiated head dimension (64); impl 2 / 1 force one of them; impl 3 = the tcgen05 kernel's reference-order
+  // variant (probabilities normalised before they are rounded, like modeling_llama.py:530-541; kv_bound must bound
+  // kv_len + q_len and fit 384 * n_splits)
+  if (impl == 3)
+    return lade::attn_fwd_tc_exact_launch((cudaStream_t)stream, q, k_cache, v_cache, out, rowmask, mask_words, meta, scratch,
+                                          q_pad, n_heads, n_kv_heads, head_dim, kv_capacity, kv_bound, n_splits, 0);
   if ((impl == 0 && head_dim == 128) || impl == 2)
     return lade::attn_fwd_tc_launch((cudaStream_t)stream, q, k_cache, v_cache, out, rowmask, mask_words, meta, scratch, q_pad,
                                     n_heads, n_kv_heads, head_dim, kv_capacity, kv_bound, n_splits, 0);
@@ -52,6 +60,9 @@ int lade_attn_fwd_f16(void* stream, const void* q, const void* k_cache, const vo
   if (rowmask && mask_words * 32 < q_pad) return LADE_EINVAL;
   if (q_pad < 1 || n_heads < 1 || n_kv_heads < 1 || n_heads % n_kv_heads != 0 || n_splits < 1 || kv_capacity < 1)
     return LADE_EINVAL;
+  if (impl == 3)
+    return lade::attn_fwd_tc_exact_launch((cudaStream_t)stream, q, k_cache, v_cache, out, rowmask, mask_words, meta, scratch,
+                                          q_pad, n_heads, n_kv_heads, head_dim, kv_capacity, kv_bound, n_splits, 1);
   if ((impl == 0 && head_dim == 128) || impl == 2)
     return lade::attn_fwd_tc_launch((cudaStream_t)stream, q, k_cache, v_cache, out, rowmask, mask_words, meta, scratch, q_pad,
                                     n_heads, n_kv_heads, head_dim, kv_capacity, kv_bound, n_splits, 1);

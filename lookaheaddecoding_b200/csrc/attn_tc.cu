@@ -562,6 +562,297 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   TC_STAMP(TS_END, 0);
 }
 
+// ---- reference-order variant (impl 3) ---------------------------------------------------------------------
+// Same tiles, same MMAs, same split over a cluster -- but the probabilities are rounded the way the reference rounds
+// them (lade/models/modeling_llama.py:530-541): p = model_dtype( exp(x - max_row) / sum_row ) with the max and the sum
+// of the WHOLE row (all KV splits), normalised in fp32 BEFORE the rounding, then P.V with fp32 accumulation.  The
+// online-softmax kernel above has to round exp(x - max_so_far) before it knows the sum, which changes the last bit of
+// about half of the outputs.  Knowing the whole row first means: every S tile of a split stays resident
+// in tensor memory (3 x 128 columns + O = the 512 columns of an SM, so at most 3 KV tiles per split), and the splits
+// of a head meet twice in the middle of the kernel (row maxima, then row sums, through an L2-resident table and a
+// cluster barrier each).  It is an opt-in parity mode (impl = 3, `LookaheadEngine(attn_impl=3)`): slower, and bounded
+// to kv_len + q_len <= 384 * n_splits.
+template <typename ET>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+attn_fwd_tc_exact_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                         const __grid_constant__ CUtensorMap tmV, ET* __restrict__ out,
+                         const uint32_t* __restrict__ rowmask, int mask_words, const int* __restrict__ meta, int q_pad,
+                         int n_heads, int n_kv_heads, int n_splits, float inv_sqrt_d, float2* __restrict__ row_ml) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int split = blockIdx.x, h = blockIdx.y, mt = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_len = meta[LADE_M_Q_LEN];
+  const int kv_len = meta[LADE_M_KV_LEN];
+  const int is_prefill = meta[LADE_M_IS_PREFILL];
+  const int T = kv_len + q_len;
+  int Tm = T;
+  if (is_prefill) Tm = min(T, kv_len + min(q_len, (mt + 1) * TC_BM));
+  const int n_tiles = (Tm + TC_BN - 1) / TC_BN;
+  const int t_base = n_tiles / n_splits, t_rem = n_tiles - t_base * n_splits;
+  const int n_active = n_tiles < n_splits ? n_tiles : n_splits;
+  const bool active = split < n_active;
+  const int tile_lo = split * t_base + (split < t_rem ? split : t_rem);
+  const int my_tiles = active ? t_base + (split < t_rem ? 1 : 0) : 0;
+  if (t_base + (t_rem ? 1 : 0) > 3) __trap();     // the caller's kv_bound was not a bound (host checks it)
+  const int hk = h / (n_heads / n_kv_heads);
+  const int HD = n_heads * TC_D;
+  const long long hm = (long long)h * gridDim.z + mt;
+  griddep_launch_dependents();
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_SMEM_TILES);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  // barrier slots: 0 q_full | 1..3 k_full | 4..6 v_full | 7..9 s_full | 10..12 p_full | 13 o_final
+  const int B_QFULL = 0, B_KFULL = 1, B_VFULL = 4, B_SFULL = 7, B_PFULL = 10, B_OFINAL = 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  ET* s_xmax = reinterpret_cast<ET*>(smem + TC_SMEM_TILES + 256);        // [4][128] row maxima of the four column quarters
+  float* s_xsum = reinterpret_cast<float*>(smem + TC_SMEM_TILES + 256);   // [4][128] row sums (after the maxima are dead)
+  const uint32_t sQ_a = smem_u32(smem);
+  auto sK_a = [&](int s) { return sQ_a + (uint32_t)TC_TILE_BYTES * (1 + 2 * s); };
+  auto sV_a = [&](int s) { return sQ_a + (uint32_t)TC_TILE_BYTES * (2 + 2 * s); };
+
+  if (active) {
+    if (threadIdx.x == 0) {
+      if ((sQ_a & 1023u) != 0) __trap();
+      mbar_init(BAR(B_QFULL), 1);
+      for (int s = 0; s < 3; ++s) {
+        mbar_init(BAR(B_KFULL + s), 1); mbar_init(BAR(B_VFULL + s), 1);
+        mbar_init(BAR(B_SFULL + s), 1); mbar_init(BAR(B_PFULL + s), TC_SOFTMAX_THREADS / 32);
+      }
+      mbar_init(BAR(B_OFINAL), 1);
+      fence_barrier_init();
+      auto issue_tile = [&](int j) {
+        const int row0 = (tile_lo + j) * TC_BN;
+        mbar_expect_tx(BAR(B_KFULL + j), TC_TILE_BYTES);
+        tma_load_3d(sK_a(j), &tmK, BAR(B_KFULL + j), 0, row0, hk);
+        tma_load_3d(sK_a(j) + TC_HALF_BYTES, &tmK, BAR(B_KFULL + j), 64, row0, hk);
+        mbar_expect_tx(BAR(B_VFULL + j), TC_TILE_BYTES);
+        tma_load_3d(sV_a(j), &tmV, BAR(B_VFULL + j), 0, row0, hk);
+        tma_load_3d(sV_a(j) + TC_HALF_BYTES, &tmV, BAR(B_VFULL + j), 64, row0, hk);
+      };
+      int n_old = 0;                                   // leading tiles that hold only rows of earlier steps
+      while (n_old < my_tiles && (tile_lo + n_old + 1) * TC_BN <= kv_len) ++n_old;
+      for (int j = 0; j < n_old; ++j) issue_tile(j);
+      griddep_wait();
+      mbar_expect_tx(BAR(B_QFULL), TC_TILE_BYTES);
+      tma_load_3d(sQ_a, &tmQ, BAR(B_QFULL), 0, mt * TC_BM, h);
+      tma_load_3d(sQ_a + TC_HALF_BYTES, &tmQ, BAR(B_QFULL), 64, mt * TC_BM, h);
+      for (int j = n_old; j < my_tiles; ++j) issue_tile(j);
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  const uint32_t tmem_base = active ? *tmem_slot : 0u;
+  const uint32_t tmem_O = tmem_base + 384;
+  float ov[32];                         // a softmax thread's share of its split's (already normalised) partial O row
+
+  if (!active || warp == 0) {
+    // nothing to compute (idle split / the producer, whose loads are all in flight): meet the cluster twice
+    cluster_arrive(); cluster_wait();
+    cluster_arrive(); cluster_wait();
+  } else if (warp == 1) {
+    constexpr uint32_t IDESC_QK = umma_idesc<ET>(false);
+    constexpr uint32_t IDESC_PV = umma_idesc<ET>(true);
+    if (lane == 0) {
+      mbar_wait(BAR(B_QFULL), 0);
+      for (int j = 0; j < my_tiles; ++j) {
+        mbar_wait(BAR(B_KFULL + j), 0);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)j * 128u;
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = umma_desc(sQ_a + kb * TC_HALF_BYTES + k * 32, 16, 1024);
+            const uint64_t db = umma_desc(sK_a(j) + kb * TC_HALF_BYTES + k * 32, 16, 1024);
+            umma_bf16(d, da, db, IDESC_QK, (kb | k) ? 1u : 0u);
+          }
+        umma_commit(BAR(B_SFULL + j));
+      }
+    }
+    __syncwarp();
+    cluster_arrive(); cluster_wait();     // row maxima of all splits
+    cluster_arrive(); cluster_wait();     // row sums of all splits
+    if (lane == 0) {
+      for (int j = 0; j < my_tiles; ++j) {
+        mbar_wait(BAR(B_PFULL + j), 0);
+        mbar_wait(BAR(B_VFULL + j), 0);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint64_t da = umma_desc(sK_a(j) + (kk >> 2) * TC_HALF_BYTES + (kk & 3) * 32, 16, 1024);
+          const uint64_t db = umma_desc(sV_a(j) + kk * 2048, TC_HALF_BYTES, 1024);
+          umma_bf16(tmem_O, da, db, IDESC_PV, (j > 0 || kk > 0) ? 1u : 0u);
+        }
+      }
+      umma_commit(BAR(B_OFINAL));
+    }
+    __syncwarp();
+  } else {
+    const int quad = warp & 3;
+    const int q4 = (warp - 2) >> 2;
+    const int row_l = quad * 32 + lane;
+    const int row = mt * TC_BM + row_l;
+    const uint32_t* mrow = (row < q_pad && !is_prefill && rowmask != nullptr) ? rowmask + (long long)row * mask_words : nullptr;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const uint32_t tS = tmem_base + lane_addr + (uint32_t)q4 * 32u;
+    float v[32];
+    uint32_t mbits[3] = {0u, 0u, 0u};
+    // ---- pass A: the row maximum of the split (the rounding and the positive scale are monotone: round the max once)
+    float mx_raw = -INFINITY;
+    for (int j = 0; j < my_tiles; ++j) {
+      mbar_wait(BAR(B_SFULL + j), 0);
+      tc_fence_after();
+      const int col0 = (tile_lo + j) * TC_BN + q4 * 32;
+      uint32_t mb = 0xffffffffu;
+      if (col0 + 32 > kv_len) mb = visible_bits32(mrow, mask_words, col0, kv_len, q_len, is_prefill, row);
+      if (j == 0) mbits[0] = mb; else if (j == 1) mbits[1] = mb; else mbits[2] = mb;
+      tmem_ld32(tS + (uint32_t)j * 128u, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mx_raw = fmaxf(mx_raw, ((mb >> i) & 1u) ? v[i] : -INFINITY);
+    }
+    s_xmax[q4 * 128 + row_l] = Elem<ET>::from_f(mx_raw == -INFINITY ? -INFINITY : round_to<ET>(mx_raw) * inv_sqrt_d);
+    named_bar_sync(1, TC_SOFTMAX_THREADS);
+    const float m_split = fmaxf(fmaxf(Elem<ET>::to_f(s_xmax[row_l]), Elem<ET>::to_f(s_xmax[128 + row_l])),
+                                fmaxf(Elem<ET>::to_f(s_xmax[256 + row_l]), Elem<ET>::to_f(s_xmax[384 + row_l])));
+    if (q4 == 0) row_ml[(hm * n_splits + split) * TC_BM + row_l].x = m_split;
+    cluster_arrive(); cluster_wait();
+    float m_all = -INFINITY;
+    for (int s = 0; s < n_active; ++s) m_all = fmaxf(m_all, ld_global_f2(row_ml + (hm * n_splits + s) * TC_BM + row_l).x);
+    const float m_ref = (m_all == -INFINITY) ? 0.f : m_all;   // x - max is exact in fp32 (both are model-dtype values)
+    // ---- pass B: e = exp(x - max) in fp32, kept in tensor memory in place of the scores; the row sum of the split
+    float l_part = 0.f;
+    for (int j = 0; j < my_tiles; ++j) {
+      const uint32_t mb = j == 0 ? mbits[0] : (j == 1 ? mbits[1] : mbits[2]);
+      tmem_ld32(tS + (uint32_t)j * 128u, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        float r0, r1;
+        round_scale_round2<ET>(v[i], v[i + 1], inv_sqrt_d, r0, r1);
+        v[i] = ((mb >> i) & 1u) ? ex2_approx((r0 - m_ref) * TC_LOG2E) : 0.f;
+        v[i + 1] = ((mb >> (i + 1)) & 1u) ? ex2_approx((r1 - m_ref) * TC_LOG2E) : 0.f;
+        l_part += v[i];
+        l_part += v[i + 1];
+      }
+      tmem_st32(tS + (uint32_t)j * 128u, v);
+      tmem_st_wait();
+    }
+    s_xsum[q4 * 128 + row_l] = l_part;      // the maxima were read by everybody before the cluster barrier above
+    named_bar_sync(1, TC_SOFTMAX_THREADS);
+    const float l_split = (s_xsum[row_l] + s_xsum[128 + row_l]) + (s_xsum[256 + row_l] + s_xsum[384 + row_l]);
+    if (q4 == 0) row_ml[(hm * n_splits + split) * TC_BM + row_l].y = l_split;
+    cluster_arrive(); cluster_wait();
+    float l_all = 0.f;
+    for (int s = 0; s < n_active; ++s) l_all += ld_global_f2(row_ml + (hm * n_splits + s) * TC_BM + row_l).y;
+    // ---- pass C: p = model_dtype(e / sum) -> the K stage (A operand of P.V), tile by tile
+    for (int j = 0; j < my_tiles; ++j) {
+      tmem_ld32(tS + (uint32_t)j * 128u, v);
+      tmem_ld_wait();
+      unsigned char* prow = smem + TC_TILE_BYTES * (1 + 2 * j) + (q4 >> 1) * TC_HALF_BYTES + row_l * 128;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float p[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) p[e] = l_all > 0.f ? __fdiv_rn(v[g * 8 + e], l_all) : 0.f;
+        uint4 pk;
+        pk.x = Elem<ET>::pack2(p[0], p[1]); pk.y = Elem<ET>::pack2(p[2], p[3]);
+        pk.z = Elem<ET>::pack2(p[4], p[5]); pk.w = Elem<ET>::pack2(p[6], p[7]);
+        const int cc = (q4 & 1) * 4 + g;
+        *reinterpret_cast<uint4*>(prow + ((cc ^ (row_l & 7)) << 4)) = pk;
+      }
+      const int tile0 = (tile_lo + j) * TC_BN;
+      if (tile0 + TC_BN > T) {                       // stale cache rows past T must not reach the MMA (0 * NaN)
+        mbar_wait(BAR(B_VFULL + j), 0);
+        if (tile0 + row_l >= T) {
+          unsigned char* pV = smem + TC_TILE_BYTES * (2 + 2 * j) + (q4 >> 1) * TC_HALF_BYTES + row_l * 128 + (q4 & 1) * 64;
+          const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4*>(pV + cc * 16) = z;
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(B_PFULL + j));
+    }
+    mbar_wait(BAR(B_OFINAL), 0);
+    tc_fence_after();
+    tmem_ld32(tmem_O + lane_addr + (uint32_t)q4 * 32u, ov);
+    tmem_ld_wait();
+    if (n_splits == 1 && row < q_pad) {
+      uint4* dst = reinterpret_cast<uint4*>(out + (long long)row * HD + h * TC_D + q4 * 32);
+#pragma unroll
+      for (int v4 = 0; v4 < 4; ++v4) {
+        uint4 pk;
+        pk.x = Elem<ET>::pack2(ov[v4 * 8 + 0], ov[v4 * 8 + 1]);
+        pk.y = Elem<ET>::pack2(ov[v4 * 8 + 2], ov[v4 * 8 + 3]);
+        pk.z = Elem<ET>::pack2(ov[v4 * 8 + 4], ov[v4 * 8 + 5]);
+        pk.w = Elem<ET>::pack2(ov[v4 * 8 + 6], ov[v4 * 8 + 7]);
+        dst[v4] = pk;
+      }
+    }
+    tc_fence_before();
+  }
+
+  if (active) {
+    __syncthreads();
+    if (warp == 1) {
+      tc_fence_after();
+      tmem_dealloc(tmem_base, 512);
+    }
+  }
+  if (n_splits == 1) return;
+
+  // ---- the partial rows of the splits are plain summands now: push to the owner, add, store (slots alias the stages)
+  const int rows_valid = min(TC_BM, q_pad - mt * TC_BM);
+  const int per = (rows_valid + n_active - 1) / n_active;
+  cluster_arrive(); cluster_wait();       // every CTA of the cluster is done with its K/V stages
+  int dest = -1, r_in = 0;
+  if (active && warp >= 2) {
+    const int row_l = (warp & 3) * 32 + lane;
+    const int q4 = (warp - 2) >> 2;
+    dest = row_l < rows_valid ? row_l / per : -2;
+    r_in = row_l - dest * per;
+    if (dest >= 0 && dest != split) {
+      const int slot = split < dest ? split : split - 1;
+      const uint32_t o_a = dsmem_addr(sQ_a + TC_TILE_BYTES + (uint32_t)(((slot * per + r_in) * TC_SO_STRIDE + q4 * 32) * 4), dest);
+#pragma unroll
+      for (int v4 = 0; v4 < 8; ++v4) st_dsmem_f4(o_a + v4 * 16, ov[v4 * 4], ov[v4 * 4 + 1], ov[v4 * 4 + 2], ov[v4 * 4 + 3]);
+    }
+  }
+  cluster_arrive(); cluster_wait();       // the pushes have landed
+  if (active && warp >= 2 && dest == split) {
+    const int row_l = (warp & 3) * 32 + lane;
+    const int q4 = (warp - 2) >> 2;
+    const int row = mt * TC_BM + row_l;
+    const float* so = reinterpret_cast<const float*>(smem + TC_TILE_BYTES);
+    for (int k = 0; k < n_active - 1; ++k) {
+      const float4* src = reinterpret_cast<const float4*>(so + (k * per + r_in) * TC_SO_STRIDE + q4 * 32);
+#pragma unroll
+      for (int v4 = 0; v4 < 8; ++v4) {
+        const float4 x = src[v4];
+        ov[v4 * 4] += x.x; ov[v4 * 4 + 1] += x.y; ov[v4 * 4 + 2] += x.z; ov[v4 * 4 + 3] += x.w;
+      }
+    }
+    if (row < q_pad) {
+      uint4* dst = reinterpret_cast<uint4*>(out + (long long)row * HD + h * TC_D + q4 * 32);
+#pragma unroll
+      for (int v4 = 0; v4 < 4; ++v4) {
+        uint4 pk;
+        pk.x = Elem<ET>::pack2(ov[v4 * 8 + 0], ov[v4 * 8 + 1]);
+        pk.y = Elem<ET>::pack2(ov[v4 * 8 + 2], ov[v4 * 8 + 3]);
+        pk.z = Elem<ET>::pack2(ov[v4 * 8 + 4], ov[v4 * 8 + 5]);
+        pk.w = Elem<ET>::pack2(ov[v4 * 8 + 6], ov[v4 * 8 + 7]);
+        dst[v4] = pk;
+      }
+    }
+  }
+}
+
 int attn_tc_set_timing_buffer(void* dev_ptr) {
   long long* p = reinterpret_cast<long long*>(dev_ptr);
   cudaError_t e = cudaMemcpyToSymbol(g_attn_timing, &p, sizeof(p));
@@ -722,6 +1013,68 @@ int attn_fwd_tc_launch(cudaStream_t stream, const void* q, const void* k_cache, 
                                         n_kv_heads, head_dim, kv_capacity, kv_bound, n_splits);
   return attn_fwd_tc_launch_t<__nv_bfloat16>(stream, q, k_cache, v_cache, out, rowmask, mask_words, meta, scratch, q_pad,
                                              n_heads, n_kv_heads, head_dim, kv_capacity, kv_bound, n_splits);
+}
+
+// impl 3: the reference-order variant.  kv_bound must bound kv_len + q_len of this call (the resident-S design holds at
+// most 3 KV tiles per split); the kernel traps if it does not.
+template <typename ET>
+static int attn_fwd_tc_exact_launch_t(cudaStream_t stream, const void* q, const void* k_cache, const void* v_cache, void* out,
+                                      const uint32_t* rowmask, int mask_words, const int32_t* meta, void* scratch, int q_pad,
+                                      int n_heads, int n_kv_heads, int head_dim, int kv_capacity, int kv_bound, int n_splits) {
+  if (head_dim != TC_D) return LADE_EUNSUPPORTED;
+  const int q_tiles = (q_pad + TC_BM - 1) / TC_BM;
+  if (n_splits > 8) n_splits = 8;
+  if (kv_bound < 1 || (kv_bound + TC_BN - 1) / TC_BN > 3 * n_splits) {
+    set_error_string("lade_attn_fwd impl 3: kv_bound exceeds 384 * n_splits (every S tile of a split must fit tensor memory)");
+    return LADE_EUNSUPPORTED;
+  }
+  if ((reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(k_cache) & 15) ||
+      (reinterpret_cast<uintptr_t>(v_cache) & 15))
+    return LADE_EINVAL;
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  if ((rc = get_tensor_map(q, q_pad, n_heads, &tmQ)) != LADE_OK) return rc;
+  if ((rc = get_tensor_map(k_cache, kv_capacity, n_kv_heads, &tmK)) != LADE_OK) return rc;
+  if ((rc = get_tensor_map(v_cache, kv_capacity, n_kv_heads, &tmV)) != LADE_OK) return rc;
+  static unsigned long long attr_devs = 0;
+  int cur_dev = 0;
+  LADE_CUDA_CHECK(cudaGetDevice(&cur_dev));
+  if (!((attr_devs >> (cur_dev & 63)) & 1ull)) {
+    LADE_CUDA_CHECK(cudaFuncSetAttribute(attn_fwd_tc_exact_kernel<ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr_devs |= 1ull << (cur_dev & 63);
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n_splits, n_heads, q_tiles);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TC_SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = n_splits;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  const float inv_sqrt_d = 1.0f / sqrtf((float)head_dim);
+  // the (max, sum) table of the rows lives where the L2 merge transport keeps its (m, l) pairs
+  float* part_o = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 65536);
+  float2* row_ml = reinterpret_cast<float2*>(part_o + (size_t)n_splits * n_heads * q_tiles * TC_BM * TC_D);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, attn_fwd_tc_exact_kernel<ET>, tmQ, tmK, tmV, (ET*)out, rowmask, mask_words, meta,
+                                     q_pad, n_heads, n_kv_heads, n_splits, inv_sqrt_d, row_ml);
+  if (e != cudaSuccess) { set_cuda_error(e, "cudaLaunchKernelEx(attn_fwd_tc_exact_kernel)"); return LADE_ECUDA; }
+  return LADE_OK;
+}
+
+int attn_fwd_tc_exact_launch(cudaStream_t stream, const void* q, const void* k_cache, const void* v_cache, void* out,
+                             const uint32_t* rowmask, int mask_words, const int32_t* meta, void* scratch, int q_pad, int n_heads,
+                             int n_kv_heads, int head_dim, int kv_capacity, int kv_bound, int n_splits, int is_f16) {
+  if (is_f16)
+    return attn_fwd_tc_exact_launch_t<__half>(stream, q, k_cache, v_cache, out, rowmask, mask_words, meta, scratch, q_pad,
+                                              n_heads, n_kv_heads, head_dim, kv_capacity, kv_bound, n_splits);
+  return attn_fwd_tc_exact_launch_t<__nv_bfloat16>(stream, q, k_cache, v_cache, out, rowmask, mask_words, meta, scratch, q_pad,
+                                                   n_heads, n_kv_heads, head_dim, kv_capacity, kv_bound, n_splits);
 }
 
 }  // namespace lade

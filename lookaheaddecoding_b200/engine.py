@@ -149,6 +149,19 @@ class LookaheadEngine:
         self.q_nonprefill = max([self.q_steady] + [int(self.lib.lade_step_rows_bound(C.byref(probe), 1, k))
                                                    for k in range(1, self.N - 1)])
         self.kv_capacity = self.max_total_len + self.q_nonprefill + self.WCAP + 8
+        # kv_bound of lade_attn_fwd: an upper bound of kv_len + q_len over the whole generation.  Only impl 3 (the
+        # reference-order variant, every S tile of a split resident in tensor memory) needs a tight one: at most
+        # 3 KV tiles of 128 rows per split and 8 splits per head
+        self.attn_kv_bound = self.kv_capacity
+        if self.attn_impl == 3:
+            self.attn_kv_bound = min(self.kv_capacity, self.max_total_len + self.q_nonprefill)
+            need = -(-((self.attn_kv_bound + 127) // 128) // 3)
+            if need > 8:
+                raise LadeError(f"attn_impl=3 holds at most 3072 rows of context (asked for {self.attn_kv_bound})")
+            if not attn_splits:
+                self.attn_splits = max(self.attn_splits, need)
+            elif self.attn_splits < need:
+                raise LadeError(f"attn_impl=3 needs attn_splits >= {need} for {self.attn_kv_bound} rows of context")
         self._fuse_weights()
         self._rope_tables()
         self._alloc(self.q_nonprefill)
@@ -324,7 +337,7 @@ class LookaheadEngine:
         o_buf, gu, act, d_buf = self.o_buf[:rows], self.gu[:rows], self.act[:rows], self.d_buf[:rows]
         qb = self.qb if rows == self.rows_cap else self.qb.view(-1)[: self.nh * rows * self.D].view(self.nh, rows, self.D)
         delta = None
-        kv_bound = self.kv_capacity
+        kv_bound = self.attn_kv_bound
         pf = self.prefetch_mb if (self.l2_prefetch and not prefill) else (0, 0, 0, 0, 0)
         for l in range(L):
             n += self._prefetch([(self.w_qkv[l], 0)], pf[0])                              # beside rmsnorm

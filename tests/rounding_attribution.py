@@ -13,6 +13,7 @@ either difference removed through the engine's checker hooks:
   B  projections issued call for call like the reference (engine._unfused_gemms)
   C  attention replaced by the restated reference math in torch on the engine's own Q / KV cache (engine._attn_hook)
   D  B + C
+  E  the engine with attn_impl=3: the tcgen05 kernel's reference-order variant (no hooks, CUDA graph on)
 
 and prints one JSON line with the number of divergences of each against the reference's own self-inconsistency on the
 same run (ids of its lookahead loop vs its own teacher-forced forward).  usage (GPU box):
@@ -32,7 +33,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--max-new", type=int, default=128)
     ap.add_argument("--prompt-len", type=int, default=1024)
-    ap.add_argument("--modes", default="A,B,C,D")
+    ap.add_argument("--modes", default="A,B,C,D,E")
     args = ap.parse_args()
 
     import numpy as np
@@ -74,10 +75,10 @@ def main():
     out = {"compared_tokens": args.max_new, "prompt_len": P,
            "reference_self_mismatches": self_rep["n_self_mismatch"], "modes": {}}
     names = {"A": "as shipped", "B": "projections call for call", "C": "reference-order attention (torch)",
-             "D": "both"}
+             "D": "both", "E": "attn_impl=3 (reference-order tcgen05 kernel)"}
     for mode in args.modes.split(","):
         eng = LookaheadEngine(model, W, N, G, pool_from_prompt=True, max_total_len=P + args.max_new + 8,
-                              use_cuda_graph=mode in ("A", "B"))
+                              use_cuda_graph=mode in ("A", "B", "E"), attn_impl=3 if mode == "E" else 0)
         eng._unfused_gemms = mode in ("B", "D")
         if mode in ("C", "D"):
             eng._attn_hook = attn_hook

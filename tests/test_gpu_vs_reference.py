@@ -54,9 +54,9 @@ def build_pair(shape, seed=0, dtype=torch.bfloat16):
     return hf, PAR.reference_model_sharing_weights(hf, shape)
 
 
-def engine_generate(hf, W, N, G, pool, cap, eos=()):
+def engine_generate(hf, W, N, G, pool, cap, eos=(), **engine_kw):
     from lookaheaddecoding_b200 import LookaheadEngine
-    eng = LookaheadEngine(hf, W, N, G, pool_from_prompt=pool, max_total_len=cap)
+    eng = LookaheadEngine(hf, W, N, G, pool_from_prompt=pool, max_total_len=cap, **engine_kw)
 
     def gen(prompt, n_new):
         return eng.generate(prompt, n_new, eos_token_ids=eos, rng=random.Random(7))
@@ -156,4 +156,19 @@ def test_fp16_engine_ids_match_reference_on_the_same_gpu(name, shape, W, N, G, P
     a = eng.generate(prompt, min(new, 24), rng=random.Random(1), sampling={"temperature": 0.8, "top_k": 40, "seed": 5})
     b = eng.generate(prompt, min(new, 24), rng=random.Random(1), sampling={"temperature": 0.8, "top_k": 40, "seed": 5})
     assert a == b and all(0 <= t < shape["vocab"] for t in a)
+    eng.close()
+
+
+@pytest.mark.parametrize("name,shape,W,N,G,P,new,pool", [c for c in CASES if c[0] in ("w15n5g15_pool", "gqa_w15n5g15", "w20n7g20_pool", "edge_p1")],
+                         ids=["w15n5g15_pool", "w20n7g20_pool", "gqa_w15n5g15", "edge_p1"])
+def test_reference_order_attention_engine_ids(name, shape, W, N, G, P, new, pool):
+    """attn_impl=3: the attention variant that rounds the probabilities like the reference, through the whole engine."""
+    hf, ref = build_pair(shape)
+    g = torch.Generator().manual_seed(1)
+    prompt = torch.randint(3, shape["vocab"], (P,), generator=g).tolist()
+    ref_ids, _ = PAR.reference_greedy(ref, prompt, new, W, N, G, py_seed=0, pool_from_prompt=pool)
+    eng, gen = engine_generate(hf, W, N, G, pool, P + new, attn_impl=3)
+    rep = PAR.compare_ids(gen, ref_ids, P, ref)
+    print(f"\n{name} (attn_impl=3): exact={rep['exact']} divergences={rep['n_divergences']}")
+    assert rep["ok"], rep
     eng.close()
