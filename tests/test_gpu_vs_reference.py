@@ -172,3 +172,18 @@ def test_reference_order_attention_engine_ids(name, shape, W, N, G, P, new, pool
     print(f"\n{name} (attn_impl=3): exact={rep['exact']} divergences={rep['n_divergences']}")
     assert rep["ok"], rep
     eng.close()
+
+
+def test_reference_order_attention_refuses_contexts_it_cannot_hold():
+    """attn_impl=3 keeps every S tile of a split in tensor memory: more than 3072 rows of context (3 tiles x 8 splits)
+    are refused when the engine is built, never silently downgraded."""
+    from bench import build_model
+    from lookaheaddecoding_b200 import LookaheadEngine
+    hf = build_model(dict(TINY, max_pos=8192), torch.device("cuda"), seed=0)
+    with pytest.raises(Exception, match="attn_impl=3"):
+        LookaheadEngine(hf, 15, 5, 15, max_total_len=4096, attn_impl=3)
+    with pytest.raises(Exception, match="attn_impl=3"):
+        LookaheadEngine(hf, 15, 5, 15, max_total_len=1024, attn_impl=3, attn_splits=2)
+    eng = LookaheadEngine(hf, 15, 5, 15, max_total_len=1024, attn_impl=3)
+    assert eng.attn_splits >= 3 and eng.attn_kv_bound <= 384 * eng.attn_splits
+    eng.close()
